@@ -1,0 +1,465 @@
+// libevc_b200: C ABI (include/evc.h) over the CUDA kernels.  One translation unit.
+//
+// Host-side control flow restates sklearn/decomposition/_nmf.py (1.9.0), the dependency that
+// holds the reference's arithmetic (04_align_n_nmf.py:212-213):
+//   _check_w_h (update_H=False, solver 'mu')      :1205-1226   -> init_activations()
+//   _fit_multiplicative_update                    :726-886     -> solve_impl() loop + stop rule
+//   _multiplicative_update_w                      :521-626     -> step_kl()/step_fro()
+//   _beta_divergence                              :78-182      -> objective()
+#include "evc_common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
+#include "nccl_shim.cuh"
+
+#include <cmath>
+#include <new>
+
+using namespace evc;
+
+struct evc_comm {
+  nccl::Comm comm;
+  int rank = 0, world = 1;
+};
+
+struct evc_dict {
+  int F = 0, N = 0, mode = 0, device = 0;
+  int n_total = 0;  // exemplars across all shards (== N when not sharded): H0 uses it (sklearn n_components)
+  bool has_target = false;
+  // fp32 mode operands
+  int ldA = 0;               // pitch of A / B copies (floats)
+  float* A = nullptr;        // (N, ldA) zero padded
+  float* B = nullptr;        // (N, ldA)
+  float* colsum = nullptr;   // A^T 1  (N)
+  tc::DictOperands tc_ops;   // tensor-core operand copies + tensor maps (modes 1..3)
+  evc_comm* comm = nullptr;  // exemplar sharding: all-reduce of partial A*H
+  // per-solve workspace, grow-only
+  DevBuf WH, R, rowd, w0, active, num0, tcws;
+  double* host_rows = nullptr;  // pinned mirror of rowd
+  size_t host_rows_cap = 0;
+  float* host_w0 = nullptr;     // pinned
+  unsigned char* host_active = nullptr;
+  size_t host_T_cap = 0;
+  int ldWH = 0, ldR = 0;
+};
+
+namespace {
+
+int reserve_workspace(evc_dict* d, int T, int ldH, bool need_num0) {
+  d->ldWH = round_up(d->F, 4);
+  d->ldR = tc::k_pitch(d->F);
+  EVC_TRY(d->WH.reserve((size_t)T * d->ldWH * sizeof(float)));
+  EVC_TRY(d->R.reserve((size_t)T * d->ldR * sizeof(float) * 2));  // R and (3xTF32) its lo part
+  EVC_TRY(d->rowd.reserve((size_t)T * sizeof(double)));
+  EVC_TRY(d->w0.reserve((size_t)T * sizeof(float)));
+  EVC_TRY(d->active.reserve((size_t)T));
+  if (need_num0) EVC_TRY(d->num0.reserve((size_t)T * ldH * sizeof(float)));
+  if ((size_t)T > d->host_T_cap) {
+    if (d->host_rows) cudaFreeHost(d->host_rows);
+    if (d->host_w0) cudaFreeHost(d->host_w0);
+    if (d->host_active) cudaFreeHost(d->host_active);
+    d->host_rows = nullptr; d->host_w0 = nullptr; d->host_active = nullptr; d->host_T_cap = 0;
+    EVC_CUDA(cudaMallocHost(&d->host_rows, (size_t)T * sizeof(double)));
+    EVC_CUDA(cudaMallocHost(&d->host_w0, (size_t)T * sizeof(float)));
+    EVC_CUDA(cudaMallocHost(&d->host_active, (size_t)T));
+    d->host_T_cap = T;
+  }
+  return EVC_OK;
+}
+
+// ---- the three contractions, dispatched on mode -------------------------------------------------
+
+// WH (T, ldWH) = H (T,N) * A (N,F)         [first contraction; sklearn :554]
+int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH, bool target, cudaStream_t s) {
+  if (d->mode == EVC_MODE_FP32) {
+    simt::EpiArgs e{};
+    e.C = WH; e.ldc = ldWH;
+    EVC_TRY((simt::launch_gemm<simt::EPI_STORE, false>(T, d->F, d->N, H, ldH, target ? d->B : d->A, d->ldA, e, s)));
+  } else {
+    EVC_TRY(tc::contract_wh(d->tc_ops, d->mode, H, ldH, T, WH, ldWH, target, &d->tcws, s));
+  }
+  if (d->comm && d->comm->world > 1) {
+    EVC_TRY(nccl::all_reduce_sum(d->comm->comm, WH, (size_t)T * ldWH, s));
+  }
+  return EVC_OK;
+}
+
+// KL: H *= (R A^T) / (A^T1 + lam)   [second contraction + multiplicative update; sklearn :585-624]
+int update_kl(evc_dict* d, const float* X, int ldX, int T, float* H, int ldH, float lam, float eps,
+              const unsigned char* row_active, cudaStream_t s) {
+  float* R = d->R.as<float>();
+  if (d->mode == EVC_MODE_FP32) {
+    dim3 g(T, ceil_div(d->ldR, 256));
+    simt::ratio_kernel<<<g, 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, R, d->ldR, T, d->F, eps);
+    EVC_LAUNCH_CHECK();
+    simt::EpiArgs e{};
+    e.C = H; e.ldc = ldH; e.colsum = d->colsum; e.lam = lam; e.eps = eps; e.row_active = row_active;
+    EVC_TRY((simt::launch_gemm<simt::EPI_MU_KL, true>(T, d->N, d->F, R, d->ldR, d->A, d->ldA, e, s)));
+    return EVC_OK;
+  }
+  return tc::update_kl(d->tc_ops, d->mode, X, ldX, T, d->WH.as<float>(), d->ldWH, R, d->ldR, H, ldH, d->colsum,
+                       lam, eps, row_active, &d->tcws, s);
+}
+
+// Frobenius: H *= NUM0 / (WH A^T + lam)   [sklearn :535-549, with A^T(A H) instead of the N x N Gram]
+int update_fro(evc_dict* d, int T, float* H, int ldH, const float* num0, float lam, float eps,
+               const unsigned char* row_active, cudaStream_t s) {
+  if (d->mode == EVC_MODE_FP32) {
+    simt::EpiArgs e{};
+    e.C = H; e.ldc = ldH; e.X = num0; e.ldx = ldH; e.lam = lam; e.eps = eps; e.row_active = row_active;
+    EVC_TRY((simt::launch_gemm<simt::EPI_MU_FRO, true>(T, d->N, d->F, d->WH.as<float>(), d->ldWH, d->A, d->ldA, e, s)));
+    return EVC_OK;
+  }
+  return tc::update_fro(d->tc_ops, d->mode, T, d->WH.as<float>(), d->ldWH, d->R.as<float>(), d->ldR, H, ldH, num0,
+                        lam, eps, row_active, &d->tcws, s);
+}
+
+// NUM0 (T, ldH) = X A^T  (Frobenius numerator, computed once: sklearn :537-543)
+int frob_numerator(evc_dict* d, const float* X, int ldX, int T, float* num0, int ldH, cudaStream_t s) {
+  if (d->mode == EVC_MODE_FP32) {
+    simt::EpiArgs e{};
+    e.C = num0; e.ldc = ldH;
+    EVC_TRY((simt::launch_gemm<simt::EPI_STORE, true>(T, d->N, d->F, X, ldX, d->A, d->ldA, e, s)));
+    return EVC_OK;
+  }
+  return tc::frob_numerator(d->tc_ops, d->mode, X, ldX, T, d->R.as<float>(), d->ldR, num0, ldH, &d->tcws, s);
+}
+
+// Per-segment objective: err[u] = sqrt(2 * sum rows) (KL) or sqrt(sum rows) (Frobenius). Synchronises.
+int objective_segments(evc_dict* d, const float* X, int ldX, int T, const float* H, int ldH, int loss, float eps,
+                       const std::vector<int>& seg, std::vector<double>& err, cudaStream_t s) {
+  EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, false, s));
+  simt::objective_rows_kernel<<<ceil_div(T, 8), 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, T, d->F, eps, loss,
+                                                            d->rowd.as<double>());
+  EVC_LAUNCH_CHECK();
+  EVC_CUDA(cudaMemcpyAsync(d->host_rows, d->rowd.p, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s));
+  EVC_CUDA(cudaStreamSynchronize(s));
+  const int nseg = (int)seg.size() - 1;
+  err.assign(nseg, 0.0);
+  for (int u = 0; u < nseg; ++u) {
+    double acc = 0.0;
+    for (int t = seg[u]; t < seg[u + 1]; ++t) acc += d->host_rows[t];
+    acc = acc > 0.0 ? acc : 0.0;  // sklearn :177 max(res, 0)
+    err[u] = (loss == EVC_LOSS_KL) ? std::sqrt(2.0 * acc) : std::sqrt(acc);
+  }
+  return EVC_OK;
+}
+
+int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n_utt, float* H, int ldH,
+               const evc_solve_params* p, int per_utterance_stop, evc_solve_result* res, cudaStream_t s) {
+  if (!d || !X || !H || !p || !t_offsets || n_utt < 1)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: null argument or n_utt < 1");
+  const int T = t_offsets[n_utt];
+  if (t_offsets[0] != 0) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: t_offsets[0] must be 0");
+  for (int u = 0; u < n_utt; ++u)
+    if (t_offsets[u + 1] < t_offsets[u]) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: t_offsets not monotone");
+  if (ldX < d->F || ldH < d->N) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: ldX < F or ldH < N");
+  if (p->loss != EVC_LOSS_KL && p->loss != EVC_LOSS_FROBENIUS)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: loss must be EVC_LOSS_KL or EVC_LOSS_FROBENIUS");
+  if (p->max_iter < 0 || p->check_every < 1 || p->tol < 0.f || p->lambda < 0.f || p->lambda_step < 0.f)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: max_iter/check_every/tol/lambda out of range");
+  const float eps = p->epsilon > 0.f ? p->epsilon : kEpsilon;
+  const int loss = p->loss;
+  if (T == 0) {
+    for (int u = 0; u < n_utt && res; ++u) res[u] = evc_solve_result{0, 0, 0.0, 0.0};
+    return EVC_OK;
+  }
+  EVC_TRY(reserve_workspace(d, T, ldH, loss == EVC_LOSS_FROBENIUS));
+  EVC_TRY(tc::check_alignment(d->mode, H, ldH));
+
+  // Stop-rule segments: per utterance, or the whole stack as one matrix (a single reference call).
+  std::vector<int> seg;
+  if (per_utterance_stop) seg.assign(t_offsets, t_offsets + n_utt + 1);
+  else seg = {0, T};
+  const int nseg = (int)seg.size() - 1;
+
+  // H0 = sqrt(mean(X_u) / n_components)   sklearn :1225-1226
+  if (p->init == EVC_INIT_SKLEARN) {
+    simt::row_sum_kernel<<<ceil_div(T, 8), 256, 0, s>>>(X, ldX, T, d->F, d->rowd.as<double>());
+    EVC_LAUNCH_CHECK();
+    EVC_CUDA(cudaMemcpyAsync(d->host_rows, d->rowd.p, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s));
+    EVC_CUDA(cudaStreamSynchronize(s));
+    for (int u = 0; u < nseg; ++u) {
+      double acc = 0.0;
+      for (int t = seg[u]; t < seg[u + 1]; ++t) acc += d->host_rows[t];
+      const int rows = seg[u + 1] - seg[u];
+      const double mean = rows > 0 ? acc / ((double)rows * d->F) : 0.0;
+      const float w0 = (float)std::sqrt(mean / (double)d->n_total);
+      for (int t = seg[u]; t < seg[u + 1]; ++t) d->host_w0[t] = w0;
+    }
+    EVC_CUDA(cudaMemcpyAsync(d->w0.p, d->host_w0, (size_t)T * sizeof(float), cudaMemcpyHostToDevice, s));
+    dim3 g(T, ceil_div(d->N, 256));
+    simt::fill_rows_kernel<<<g, 256, 0, s>>>(H, ldH, T, d->N, d->w0.as<float>());
+    EVC_LAUNCH_CHECK();
+  } else if (p->init != EVC_INIT_GIVEN) {
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: init must be EVC_INIT_SKLEARN or EVC_INIT_GIVEN");
+  }
+  EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
+
+  std::vector<double> err0, err, prev;
+  EVC_TRY(objective_segments(d, X, ldX, T, H, ldH, loss, eps, seg, err0, s));  // sklearn :822
+  prev = err0;
+  std::vector<int> n_iter(nseg, p->max_iter), conv(nseg, 0);
+  std::vector<char> active(nseg, 1);
+  int n_active = nseg;
+  bool any_frozen = false;
+
+  float* num0 = d->num0.as<float>();
+  if (loss == EVC_LOSS_FROBENIUS) EVC_TRY(frob_numerator(d, X, ldX, T, num0, ldH, s));
+
+  for (int k = 1; k <= p->max_iter && n_active > 0; ++k) {
+    const float lam = p->lambda + (float)k * p->lambda_step;
+    const unsigned char* mask = any_frozen ? d->active.as<unsigned char>() : nullptr;
+    EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, false, s));
+    if (loss == EVC_LOSS_KL) EVC_TRY(update_kl(d, X, ldX, T, H, ldH, lam, eps, mask, s));
+    else EVC_TRY(update_fro(d, T, H, ldH, num0, lam, eps, mask, s));
+
+    if (p->tol > 0.f && k % p->check_every == 0) {  // sklearn :867-879
+      EVC_TRY(objective_segments(d, X, ldX, T, H, ldH, loss, eps, seg, err, s));
+      bool changed = false;
+      for (int u = 0; u < nseg; ++u) {
+        if (!active[u]) continue;
+        if ((prev[u] - err[u]) / err0[u] < (double)p->tol) {
+          active[u] = 0; conv[u] = 1; n_iter[u] = k; --n_active; changed = true;
+        }
+        prev[u] = err[u];
+      }
+      if (changed && n_active > 0) {
+        for (int u = 0; u < nseg; ++u)
+          memset(d->host_active + seg[u], active[u] ? 1 : 0, (size_t)(seg[u + 1] - seg[u]));
+        EVC_CUDA(cudaMemcpyAsync(d->active.p, d->host_active, (size_t)T, cudaMemcpyHostToDevice, s));
+        any_frozen = true;
+      }
+    }
+  }
+
+  if (res) {
+    EVC_TRY(objective_segments(d, X, ldX, T, H, ldH, loss, eps, seg, err, s));
+    for (int u = 0; u < n_utt; ++u) {
+      const int q = per_utterance_stop ? u : 0;
+      res[u].n_iter = n_iter[q];
+      res[u].converged = conv[q];
+      res[u].objective = err[q];
+      res[u].objective_at_init = err0[q];
+    }
+  }
+  return EVC_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+
+extern "C" {
+
+int evc_version(void) { return EVC_VERSION; }
+const char* evc_last_error_string(void) { return g_err; }
+long long evc_kernel_launch_count(void) { return g_launches.load(); }
+
+void evc_default_params(evc_solve_params* p) {
+  if (!p) return;
+  p->loss = EVC_LOSS_KL;
+  p->init = EVC_INIT_SKLEARN;
+  p->max_iter = 150;
+  p->check_every = 10;
+  p->tol = 1e-4f;
+  p->lambda = 0.f;
+  p->lambda_step = 0.f;
+  p->epsilon = 0.f;
+}
+
+int evc_dict_destroy(evc_dict_t d) {
+  if (!d) return EVC_OK;
+  cudaFree(d->A); cudaFree(d->B); cudaFree(d->colsum);
+  d->tc_ops.release();
+  d->WH.release(); d->R.release(); d->rowd.release(); d->w0.release(); d->active.release();
+  d->num0.release(); d->tcws.release();
+  if (d->host_rows) cudaFreeHost(d->host_rows);
+  if (d->host_w0) cudaFreeHost(d->host_w0);
+  if (d->host_active) cudaFreeHost(d->host_active);
+  delete d;
+  return EVC_OK;
+}
+
+int evc_dict_create(const float* A, int ldA, const float* B, int ldB, int F, int N, int mode, void* stream,
+                    evc_dict_t* out) {
+  if (!out) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_create: out is null");
+  *out = nullptr;
+  if (!A || F < 1 || N < 1 || ldA < F || (B && ldB < F))
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_create: bad shape (F=%d N=%d ldA=%d ldB=%d)", F, N, ldA, ldB);
+  if (mode < EVC_MODE_FP32 || mode > EVC_MODE_BF16)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_create: unknown mode %d", mode);
+  cudaStream_t s = (cudaStream_t)stream;
+  evc_dict* d = new (std::nothrow) evc_dict();
+  if (!d) return fail(EVC_ERR_CUDA, "evc_dict_create: out of host memory");
+  d->F = F; d->N = N; d->n_total = N; d->mode = mode; d->has_target = (B != nullptr);
+  int st = [&]() -> int {
+    EVC_CUDA(cudaGetDevice(&d->device));
+    if (mode != EVC_MODE_FP32) EVC_TRY(tc::check_device(d->device));
+    d->ldA = tc::k_pitch(F);
+    const size_t bytes = (size_t)N * d->ldA * sizeof(float);
+    EVC_CUDA(cudaMalloc(&d->A, bytes));
+    EVC_CUDA(cudaMalloc(&d->colsum, (size_t)N * sizeof(float)));
+    dim3 g(N, ceil_div(d->ldA, 256));
+    simt::repitch_kernel<<<g, 256, 0, s>>>(A, ldA, d->A, d->ldA, N, F);
+    EVC_LAUNCH_CHECK();
+    if (B) {
+      EVC_CUDA(cudaMalloc(&d->B, bytes));
+      simt::repitch_kernel<<<g, 256, 0, s>>>(B, ldB, d->B, d->ldA, N, F);
+      EVC_LAUNCH_CHECK();
+    }
+    int* flags = nullptr;
+    EVC_CUDA(cudaMalloc(&flags, 2 * sizeof(int)));
+    EVC_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), s));
+    simt::colsum_kernel<<<ceil_div(N, 8), 256, 0, s>>>(d->A, d->ldA, N, F, d->colsum, flags);
+    EVC_LAUNCH_CHECK();
+    int hflags[2] = {0, 0};
+    EVC_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(hflags), cudaMemcpyDeviceToHost, s));
+    EVC_CUDA(cudaStreamSynchronize(s));
+    cudaFree(flags);
+    // sklearn _check_init / check_non_negative (_nmf.py:61-76): ValueError on negative or all-zero dictionary
+    if (hflags[0]) return fail(EVC_ERR_VALUE, "Negative values in data passed to NMF (input H)");
+    if (!hflags[1]) return fail(EVC_ERR_VALUE, "Array passed to NMF (input H) is full of zeros.");
+    if (mode != EVC_MODE_FP32) EVC_TRY(tc::build_operands(&d->tc_ops, mode, d->A, d->B, d->ldA, F, N, s));
+    return EVC_OK;
+  }();
+  if (st != EVC_OK) {
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    evc_dict_destroy(d);
+    memcpy(g_err, keep, sizeof(keep));
+    return st;
+  }
+  *out = d;
+  return EVC_OK;
+}
+
+int evc_dict_info(evc_dict_t d, int* F, int* N, int* mode, int* has_target) {
+  if (!d) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_info: null handle");
+  if (F) *F = d->F;
+  if (N) *N = d->N;
+  if (mode) *mode = d->mode;
+  if (has_target) *has_target = d->has_target ? 1 : 0;
+  return EVC_OK;
+}
+
+int evc_dict_colsum(evc_dict_t d, float* out, void* stream) {
+  if (!d || !out) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_colsum: null argument");
+  EVC_CUDA(cudaMemcpyAsync(out, d->colsum, (size_t)d->N * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return EVC_OK;
+}
+
+int evc_solve(evc_dict_t d, const float* X, int ldX, int T, float* H, int ldH, const evc_solve_params* p,
+              evc_solve_result* res, void* stream) {
+  if (T < 0) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: T < 0");
+  const int off[2] = {0, T};
+  return solve_impl(d, X, ldX, off, 1, H, ldH, p, 0, res, (cudaStream_t)stream);
+}
+
+int evc_solve_batched(evc_dict_t d, const float* X, int ldX, const int* t_offsets, int n_utt, float* H, int ldH,
+                      const evc_solve_params* p, int per_utterance_stop, evc_solve_result* res, void* stream) {
+  return solve_impl(d, X, ldX, t_offsets, n_utt, H, ldH, p, per_utterance_stop, res, (cudaStream_t)stream);
+}
+
+static int product_impl(evc_dict_t d, const float* H, int ldH, int T, float* Y, int ldY, bool target, void* stream,
+                        const char* who) {
+  if (!d || !H || !Y || T < 0) return fail(EVC_ERR_INVALID_ARGUMENT, "%s: null argument", who);
+  if (target && !d->has_target)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "%s: dictionary was created without a target B", who);
+  if (ldH < d->N || ldY < d->F) return fail(EVC_ERR_INVALID_ARGUMENT, "%s: ldH < N or ldY < F", who);
+  if (T == 0) return EVC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  EVC_TRY(tc::check_alignment(d->mode, H, ldH));
+  EVC_TRY(reserve_workspace(d, T, ldH, false));
+  EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
+  EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, target, s));
+  EVC_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldY * sizeof(float), d->WH.p, (size_t)d->ldWH * sizeof(float),
+                             (size_t)d->F * sizeof(float), T, cudaMemcpyDeviceToDevice, s));
+  return EVC_OK;
+}
+
+int evc_convert(evc_dict_t d, const float* H, int ldH, int T, float* Y, int ldY, void* stream) {
+  return product_impl(d, H, ldH, T, Y, ldY, true, stream, "evc_convert");
+}
+
+int evc_reconstruct(evc_dict_t d, const float* H, int ldH, int T, float* WH, int ldWH, void* stream) {
+  return product_impl(d, H, ldH, T, WH, ldWH, false, stream, "evc_reconstruct");
+}
+
+int evc_objective(evc_dict_t d, const float* X, int ldX, int T, const float* H, int ldH, int loss, float epsilon,
+                  double* out, void* stream) {
+  if (!d || !X || !H || !out || T < 1) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: bad argument");
+  if (loss != EVC_LOSS_KL && loss != EVC_LOSS_FROBENIUS) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: bad loss");
+  cudaStream_t s = (cudaStream_t)stream;
+  EVC_TRY(reserve_workspace(d, T, ldH, false));
+  EVC_TRY(tc::check_alignment(d->mode, H, ldH));
+  EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
+  std::vector<int> seg = {0, T};
+  std::vector<double> err;
+  EVC_TRY(objective_segments(d, X, ldX, T, H, ldH, loss, epsilon > 0.f ? epsilon : kEpsilon, seg, err, s));
+  *out = err[0];
+  return EVC_OK;
+}
+
+int evc_factorize_convert_host(evc_dict_t d, const float* X, int ldX, int T, float* H, int ldH, float* Y, int ldY,
+                               const evc_solve_params* p, evc_solve_result* res, void* stream) {
+  if (!d || !X || !p || T < 0) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_factorize_convert_host: null argument");
+  if (ldX < d->F || (H && ldH < d->N) || (Y && ldY < d->F))
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_factorize_convert_host: pitch smaller than the row length");
+  if (Y && !d->has_target) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_factorize_convert_host: no target dictionary");
+  if (p->init == EVC_INIT_GIVEN && !H) return fail(EVC_ERR_INVALID_ARGUMENT, "init = GIVEN needs H");
+  if (T == 0) return EVC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int ldXd = round_up(d->F, 4), ldHd = round_up(d->N, 4), ldYd = round_up(d->F, 4);
+  float *dX = nullptr, *dH = nullptr, *dY = nullptr;
+  int st = [&]() -> int {
+    EVC_CUDA(cudaMalloc(&dX, (size_t)T * ldXd * sizeof(float)));
+    EVC_CUDA(cudaMalloc(&dH, (size_t)T * ldHd * sizeof(float)));
+    EVC_CUDA(cudaMemcpy2DAsync(dX, (size_t)ldXd * 4, X, (size_t)ldX * 4, (size_t)d->F * 4, T, cudaMemcpyHostToDevice, s));
+    if (p->init == EVC_INIT_GIVEN)
+      EVC_CUDA(cudaMemcpy2DAsync(dH, (size_t)ldHd * 4, H, (size_t)ldH * 4, (size_t)d->N * 4, T, cudaMemcpyHostToDevice, s));
+    EVC_TRY(evc_solve(d, dX, ldXd, T, dH, ldHd, p, res, s));
+    if (Y) {
+      EVC_CUDA(cudaMalloc(&dY, (size_t)T * ldYd * sizeof(float)));
+      EVC_TRY(evc_convert(d, dH, ldHd, T, dY, ldYd, s));
+      EVC_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldY * 4, dY, (size_t)ldYd * 4, (size_t)d->F * 4, T, cudaMemcpyDeviceToHost, s));
+    }
+    if (H)
+      EVC_CUDA(cudaMemcpy2DAsync(H, (size_t)ldH * 4, dH, (size_t)ldHd * 4, (size_t)d->N * 4, T, cudaMemcpyDeviceToHost, s));
+    EVC_CUDA(cudaStreamSynchronize(s));
+    return EVC_OK;
+  }();
+  cudaFree(dX); cudaFree(dH); cudaFree(dY);
+  return st;
+}
+
+int evc_comm_unique_id(char id_out[128]) { return nccl::unique_id(id_out); }
+
+int evc_comm_create(const char id[128], int rank, int world, evc_comm_t* out) {
+  if (!out || !id || world < 1 || rank < 0 || rank >= world)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_comm_create: bad argument");
+  evc_comm* c = new (std::nothrow) evc_comm();
+  if (!c) return fail(EVC_ERR_CUDA, "out of host memory");
+  c->rank = rank; c->world = world;
+  int st = nccl::init_rank(&c->comm, id, rank, world);
+  if (st != EVC_OK) { delete c; return st; }
+  *out = c;
+  return EVC_OK;
+}
+
+int evc_comm_destroy(evc_comm_t c) {
+  if (!c) return EVC_OK;
+  nccl::destroy(c->comm);
+  delete c;
+  return EVC_OK;
+}
+
+int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total) {
+  if (!d) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_attach_comm: null handle");
+  if (c && n_total < d->N) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_attach_comm: n_total < local N");
+  d->comm = c;
+  d->n_total = c ? n_total : d->N;
+  return EVC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+/*
+ * evc.h -- C ABI of the B200-native activation-estimation path (libevc_b200.so).
+ *
+ * The reference (entn-at/exemplars_vc) has no FFI: its boundary is the Python call
+ *
+ *   _W, _H, n_iter = non_negative_factorization(X=X, H=W, init="custom", update_H=False,
+ *                        n_components=W.shape[0], beta_loss=..., solver='mu', tol=tol,
+ *                        max_iter=150)                        04_align_n_nmf.py:212-213
+ *   converted = np.matmul(H.T, B)                             04_align_n_nmf.py:391
+ *
+ * The entry points below are what a binding for that seam calls (INTEGRATION.md shows the
+ * ctypes stub).  Conventions: plain C symbols, int status return (0 = ok), no exceptions
+ * cross the boundary, every matrix is ROW-MAJOR IN THE REFERENCE'S ORIENTATION (frames and
+ * exemplars are rows):
+ *
+ *     X (T,F) frames          == conv_sp / conv_stft      04_align_n_nmf.py:231,315
+ *     A (N,F) source dict     == A_sp / W of _factorize   04_align_n_nmf.py:242,194
+ *     B (N,F) target dict     == B_sp / B_stft            04_align_n_nmf.py:359,390
+ *     H (T,N) activations     == sklearn's W (_W); the reference returns the view _W.T
+ *     Y (T,F) converted       == H.T @ B                  04_align_n_nmf.py:391
+ *
+ * Unless a function name ends in _host, all data pointers are DEVICE pointers owned by
+ * the caller, and the call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ * except where it must read a scalar back (evc_solve with tol > 0 synchronises the stream
+ * every `check_every` iterations, like the reference's stop rule, sklearn _nmf.py:867-879).
+ * A handle must not be used from two host threads at once; distinct handles are independent.
+ */
+#ifndef EVC_H_
+#define EVC_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVC_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef struct evc_dict* evc_dict_t;
+typedef struct evc_comm* evc_comm_t;
+
+enum evc_status {
+  EVC_OK = 0,
+  EVC_ERR_INVALID_ARGUMENT = 1, /* bad shape / null pointer / bad enum               */
+  EVC_ERR_CUDA = 2,             /* a CUDA runtime/driver call failed                  */
+  EVC_ERR_UNSUPPORTED = 3,      /* mode not available for this shape / device         */
+  EVC_ERR_VALUE = 4,            /* negative or all-zero dictionary (sklearn _nmf.py:61-76 raises ValueError) */
+  EVC_ERR_COMM = 5              /* NCCL failure or libnccl not loadable               */
+};
+
+/* Arithmetic of the two contractions A*H and A^T*R (and of Y = B*H). */
+enum evc_mode {
+  EVC_MODE_FP32 = 0,   /* fp32 FFMA on CUDA cores: exact fp32, any shape (also F = 1, the f0 track) */
+  EVC_MODE_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split of both operands, 3 MMAs per product: fp32-accurate */
+  EVC_MODE_TF32 = 2,   /* tcgen05 kind::tf32, one MMA per product: fast mode                           */
+  EVC_MODE_BF16 = 3    /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate): fast mode                */
+};
+
+enum evc_loss {
+  EVC_LOSS_KL = 1,       /* beta = 1, sklearn _nmf.py:551-591 : H <- H * A^T(X / AH) / (A^T 1 + lambda)      */
+  EVC_LOSS_FROBENIUS = 2 /* beta = 2, sklearn _nmf.py:535-549 : H <- H * A^T X / (A^T (A H) + lambda)        */
+};
+
+/* How H is initialised. */
+enum evc_init {
+  EVC_INIT_SKLEARN = 0, /* H0 = sqrt(mean(X)/N) everywhere (sklearn _nmf.py:1224-1226)          */
+  EVC_INIT_GIVEN = 1    /* H holds the caller's initial activations (nmf_tool/nmf.py:28-31 style) */
+};
+
+typedef struct evc_solve_params {
+  int loss;          /* enum evc_loss                                                                */
+  int init;          /* enum evc_init                                                                */
+  int max_iter;      /* reference: 150 (04_align_n_nmf.py:213)                                       */
+  int check_every;   /* objective / stop rule period; reference: 10 (sklearn _nmf.py:867)            */
+  float tol;         /* stop when (prev - err) / err_init < tol; 0 disables (sklearn _nmf.py:867-879) */
+  float lambda;      /* constant L1 penalty added to the denominator (north star formula)            */
+  float lambda_step; /* extra penalty added per iteration: den_k = A^T1 + lambda + k*lambda_step.
+                        lambda = 0, lambda_step = l1_reg_W reproduces sklearn 1.9.0's in-place
+                        accumulation; 0 for the north-star formula            */
+  float epsilon;     /* clamp for A*H and for a zero denominator; <= 0 selects the reference's
+                        value 1.1920929e-07 (sklearn _nmf.py:32)                                      */
+} evc_solve_params;
+
+typedef struct evc_solve_result {
+  int n_iter;               /* iterations run (1-based count at break, else max_iter)   */
+  int converged;            /* 1 when the stop rule fired                               */
+  double objective;         /* sqrt(2 KL(X || H^T A)) or ||X - H^T A||_F of the result  */
+  double objective_at_init; /* the same for H0                                          */
+} evc_solve_result;
+
+int evc_version(void);
+/* Thread-local message for the last non-zero status returned on this thread. */
+const char* evc_last_error_string(void);
+
+/* Fill `p` with the reference's defaults: KL, sklearn init, max_iter 150, check 10, tol 1e-4, lambda 0. */
+void evc_default_params(evc_solve_params* p);
+
+/*
+ * Make a device-resident dictionary from A (N,F) (row pitch ldA floats) and optionally the
+ * paired target dictionary B (N,F) (row pitch ldB): re-pitches them for TMA, builds the
+ * transposed / hi-lo / bf16 operand copies the mode needs, and computes A^T 1
+ * (sklearn's cached H_sum, _nmf.py:588-590).  Replaces the per-call
+ * `A_sp = np.asarray(A_sp)` staging of 04_align_n_nmf.py:230-246.  Synchronises `stream`
+ * once to validate A >= 0 and not all-zero (sklearn _nmf.py:61-76 -> EVC_ERR_VALUE).
+ */
+int evc_dict_create(const float* A, int ldA, const float* B, int ldB, int F, int N, int mode,
+                    void* stream, evc_dict_t* out);
+int evc_dict_destroy(evc_dict_t d);
+int evc_dict_info(evc_dict_t d, int* F, int* N, int* mode, int* has_target);
+/* Copy A^T 1 (N floats) to a device buffer. */
+int evc_dict_colsum(evc_dict_t d, float* out, void* stream);
+
+/*
+ * Activation solve: replaces the sklearn call at 04_align_n_nmf.py:212-213.
+ * X (T,F) pitch ldX; H (T,N) pitch ldH is written (and read first when init = GIVEN).
+ */
+int evc_solve(evc_dict_t d, const float* X, int ldX, int T, float* H, int ldH,
+              const evc_solve_params* p, evc_solve_result* res, void* stream);
+
+/*
+ * Batched-utterance solve: X_stacked holds n_utt utterances stacked along T;
+ * utterance u owns rows [t_offsets[u], t_offsets[u+1]) (host array of n_utt+1 ints).
+ * Each utterance gets its own H0 (from its own mean) and, when per_utterance_stop != 0, its
+ * own stop decision exactly as n_utt separate reference calls would; `res` has n_utt entries.
+ */
+int evc_solve_batched(evc_dict_t d, const float* X_stacked, int ldX, const int* t_offsets, int n_utt,
+                      float* H, int ldH, const evc_solve_params* p, int per_utterance_stop,
+                      evc_solve_result* res, void* stream);
+
+/* Conversion product Y (T,F) = H (T,N) * B (N,F): 04_align_n_nmf.py:391. */
+int evc_convert(evc_dict_t d, const float* H, int ldH, int T, float* Y, int ldY, void* stream);
+
+/* Reconstruction WH (T,F) = H (T,N) * A (N,F): the first contraction on its own; the reference forms it for
+ * the residual log(H^T A - X) at 04_align_n_nmf.py:292-294. */
+int evc_reconstruct(evc_dict_t d, const float* H, int ldH, int T, float* WH, int ldWH, void* stream);
+
+/* sqrt(2 KL) / Frobenius objective of a given H (sklearn _beta_divergence, _nmf.py:78-182). Synchronises. */
+int evc_objective(evc_dict_t d, const float* X, int ldX, int T, const float* H, int ldH, int loss,
+                  float epsilon, double* out, void* stream);
+
+/*
+ * Host-buffer convenience: X, H, Y are HOST pointers (H and/or Y may be NULL to skip the
+ * copy back).  Does H2D, evc_solve, evc_convert (if Y != NULL and the dictionary has a
+ * target) and D2H on `stream`, then synchronises.
+ */
+int evc_factorize_convert_host(evc_dict_t d, const float* X, int ldX, int T, float* H, int ldH,
+                               float* Y, int ldY, const evc_solve_params* p, evc_solve_result* res,
+                               void* stream);
+
+/*
+ * Exemplar (N) sharding across GPUs: each rank builds its dictionary from its own rows
+ * A[n_begin:n_end], attaches a communicator, and evc_solve / evc_convert / evc_objective
+ * then all-reduce the partial A*H (T,F) inside the loop.  The NCCL library
+ * is the one already loaded in the process (libnccl.so.2), resolved with dlopen.
+ */
+int evc_comm_unique_id(char id_out[128]);
+int evc_comm_create(const char id[128], int rank, int world, evc_comm_t* out);
+int evc_comm_destroy(evc_comm_t c);
+int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total);
+
+/* Diagnostics: number of kernels this library has launched in this process. */
+long long evc_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVC_H_ */

@@ -1,0 +1,113 @@
+"""The oracle against the reference's own outputs (CPU).  Pins the checker before it is trusted:
+tests/golden/*.npz were produced by the reference's exact scikit-learn call (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden_inputs, load_golden, rel_fro
+from oracle import nmf_oracle as o
+
+KL_CASES = ["kl_13x32x8_tol1e-2", "kl_13x32x8_tol1e-3", "kl_13x32x8_tol1e-4", "kl_13x32x8_tol0_500",
+            "kl_13x32x8_f32", "kl_513x2000x64_tol1e-4", "kl_201x777x37_tol1e-4", "kl_edge_zeros", "kl_edge_f0"]
+
+
+@pytest.mark.parametrize("name", KL_CASES)
+def test_kl_restatement_matches_reference_output(name):
+    g = load_golden(name)
+    X, A, B = golden_inputs(g)
+    W, n_iter, obj = o.kl_mu(X, A, tol=float(g["tol"]), max_iter=int(g["max_iter"]))
+    assert n_iter == int(g["n_iter"])
+    # same BLAS, same order of operations: identical up to the last bits
+    np.testing.assert_allclose(W, g["W"], rtol=1e-9 if X.dtype == np.float64 else 1e-5, atol=0)
+    np.testing.assert_allclose(obj, float(g["objective"]), rtol=1e-7 if X.dtype == np.float64 else 1e-3)
+    np.testing.assert_allclose(o.convert(W, B), g["Y"], rtol=1e-9 if X.dtype == np.float64 else 1e-5)
+
+
+def test_survey_known_answer_table():
+    """values recorded during the survey from sklearn 1.9.0 (float64, KL, lambda = 0)."""
+    X, A, B = o.gen(20190123, 13, 32, 8)
+    assert abs(X.sum() - 2.3239120916e+02) < 1e-6 and abs(A.sum() - 4.3037000814e+02) < 1e-6
+    W0 = o.initial_activation(X, 32)
+    assert abs(W0[0, 0] - 0.26425194283181025) < 1e-15
+    assert abs(o.kl_objective(X, W0, A) - 28.552161128782707) < 1e-10
+    table = [(1e-2, 150, 40, 9.1014002625e-01, 1.6956426558e+01), (1e-3, 150, 120, 3.7807013311e-01, 1.7169381822e+01),
+             (1e-4, 150, 150, 3.1988167812e-01, 1.7198190310e+01), (0.0, 500, 500, 1.4890424243e-01, 1.7277834608e+01)]
+    for tol, mi, n_exp, obj_exp, sum_exp in table:
+        W, n, obj = o.kl_mu(X, A, tol=tol, max_iter=mi)
+        assert n == n_exp
+        assert abs(obj - obj_exp) / obj_exp < 1e-7
+        assert abs(W.sum() - sum_exp) / sum_exp < 1e-7
+    W, n, obj = o.kl_mu(X, A, tol=1e-4, max_iter=150)
+    assert abs(W[0, 0] - 8.7677399402e-02) / 8.7677399402e-02 < 1e-7
+    assert abs(np.linalg.norm(W) - 2.5967513177e+00) / 2.5967513177e+00 < 1e-7
+    assert abs(np.linalg.norm(o.convert(W, B)) - 2.6466200731e+01) / 2.6466200731e+01 < 1e-7
+
+
+def test_survey_table_513():
+    g = load_golden("kl_513x2000x64_tol0_500")
+    assert int(g["n_iter"]) == 500
+    assert abs(float(g["objective"]) - 8.6895056941e-01) / 8.6895056941e-01 < 1e-7
+    assert abs(float(g["sum_W"]) - 1.6001907294e+02) / 1.6001907294e+02 < 1e-7
+    assert abs(float(g["norm_Y"]) - 5.7751667606e+02) / 5.7751667606e+02 < 1e-7
+
+
+@pytest.mark.parametrize("name", ["fro_13x32x8_tol1e-4", "fro_201x777x37_tol1e-4"])
+def test_frobenius_restatement(name):
+    g = load_golden(name)
+    X, A, B = golden_inputs(g)
+    W, n_iter, obj = o.frobenius_mu(X, A, tol=float(g["tol"]), max_iter=int(g["max_iter"]))
+    assert n_iter == int(g["n_iter"])
+    np.testing.assert_allclose(W, g["W"], rtol=1e-9)
+    np.testing.assert_allclose(obj, float(g["objective"]), rtol=1e-9)
+
+
+def test_l1_quirk_q1_and_constant_lambda():
+    g = load_golden("kl_l1_sklearn_q1")
+    X, A = g["X"], g["A"]
+    lam = X.shape[1] * float(g["alpha_W"]) * float(g["l1_ratio"])
+    W_acc, n, _ = o.kl_mu(X, A, lam=lam, tol=0.0, max_iter=int(g["max_iter"]), sklearn_l1_accumulate=True)
+    np.testing.assert_allclose(W_acc, g["W"], rtol=1e-9)       # sklearn's denominator grows by lam each iteration
+    W_const, _, _ = o.kl_mu(X, A, lam=lam, tol=0.0, max_iter=int(g["max_iter"]))
+    assert rel_fro(W_const, g["W"]) > 1e-2                      # ... the north-star constant penalty does not
+    gc = load_golden("kl_l1_constant")
+    np.testing.assert_allclose(W_const, gc["W"], rtol=1e-12)
+
+
+def test_reference_call_is_the_restatement():
+    pytest.importorskip("sklearn")
+    X, A, _ = o.gen(77, 29, 50, 11)
+    W_ref, n_ref = o.reference_call(X, A, tol=1e-4, max_iter=60)
+    W, n, _ = o.kl_mu(X, A, tol=1e-4, max_iter=60)
+    assert n == n_ref and np.array_equal(W, W_ref)
+    W_ref, n_ref = o.reference_call(X, A, beta_loss="frobenius", tol=1e-4, max_iter=60)
+    W, n, _ = o.frobenius_mu(X, A, tol=1e-4, max_iter=60)
+    assert n == n_ref and np.array_equal(W, W_ref)
+
+
+def test_objective_masks_small_x():
+    X, A, _ = o.gen(5, 7, 9, 4)
+    X[0, 0] = 0.0
+    X[1, 2] = 1e-9          # below float32 eps: excluded from X log(X/WH) and from -sum X
+    W = o.initial_activation(X, 9)
+    WH = W @ A
+    m = X > o.EPSILON
+    expect = np.sqrt(2 * (np.sum(X[m] * np.log(X[m] / WH[m])) - X[m].sum() + WH.sum()))
+    assert abs(o.kl_objective(X, W, A) - expect) < 1e-12
+
+
+def test_nmf_tool_restatement_decreases_cost():
+    rng = np.random.default_rng(3)
+    W = rng.random((12, 5)); V = W @ rng.random((5, 7)); H0 = rng.random((5, 7))
+    costs = [o.nmf_tool_euclidean_mu(V, W, H0, k)[1] for k in (0, 1, 5, 50)]
+    assert all(b <= a + 1e-12 for a, b in zip(costs, costs[1:])) and costs[-1] < 1e-1 * costs[0]
+
+
+def test_synth_generator_matches_oracle_gen():
+    from exemplars_vc_b200 import synth
+    X, A, B = o.gen(123, 11, 40, 6, np.float32)
+    A2, B2 = synth.dictionaries(123, 11, 40)
+    assert np.array_equal(A, A2) and np.array_equal(B, B2)
+    A64, _ = synth.dictionaries(123, 11, 40, np.float64)
+    X2 = synth.frames(123, A64, 6, np.float32, exact=True)
+    assert np.array_equal(X, X2)
+    X3 = synth.frames(123, A2, 6)
+    assert X3.shape == X.shape and X3.min() > 0
