@@ -40,6 +40,7 @@ struct evc_dict {
   unsigned char* host_active = nullptr;
   size_t host_T_cap = 0;
   int ldWH = 0, ldR = 0;
+  Profiler prof;
 };
 
 namespace {
@@ -71,6 +72,7 @@ int reserve_workspace(evc_dict* d, int T, int ldH, bool need_num0) {
 // WH (T, ldWH) = H (T,N) * A (N,F)         [first contraction; sklearn :554]
 int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH, bool target, cudaStream_t s) {
   if (d->mode == EVC_MODE_FP32) {
+    ProfScope ps(0, s);
     simt::EpiArgs e{};
     e.C = WH; e.ldc = ldWH;
     EVC_TRY((simt::launch_gemm<simt::EPI_STORE, false>(T, d->F, d->N, H, ldH, target ? d->B : d->A, d->ldA, e, s)));
@@ -88,9 +90,13 @@ int update_kl(evc_dict* d, const float* X, int ldX, int T, float* H, int ldH, fl
               const unsigned char* row_active, cudaStream_t s) {
   float* R = d->R.as<float>();
   if (d->mode == EVC_MODE_FP32) {
-    dim3 g(T, ceil_div(d->ldR, 256));
-    simt::ratio_kernel<<<g, 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, R, d->ldR, T, d->F, eps);
-    EVC_LAUNCH_CHECK();
+    {
+      ProfScope ps(1, s);
+      dim3 g(T, ceil_div(d->ldR, 256));
+      simt::ratio_kernel<<<g, 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, R, d->ldR, T, d->F, eps);
+      EVC_LAUNCH_CHECK();
+    }
+    ProfScope ps(2, s);
     simt::EpiArgs e{};
     e.C = H; e.ldc = ldH; e.colsum = d->colsum; e.lam = lam; e.eps = eps; e.row_active = row_active;
     EVC_TRY((simt::launch_gemm<simt::EPI_MU_KL, true>(T, d->N, d->F, R, d->ldR, d->A, d->ldA, e, s)));
@@ -104,6 +110,7 @@ int update_kl(evc_dict* d, const float* X, int ldX, int T, float* H, int ldH, fl
 int update_fro(evc_dict* d, int T, float* H, int ldH, const float* num0, float lam, float eps,
                const unsigned char* row_active, cudaStream_t s) {
   if (d->mode == EVC_MODE_FP32) {
+    ProfScope ps(2, s);
     simt::EpiArgs e{};
     e.C = H; e.ldc = ldH; e.X = num0; e.ldx = ldH; e.lam = lam; e.eps = eps; e.row_active = row_active;
     EVC_TRY((simt::launch_gemm<simt::EPI_MU_FRO, true>(T, d->N, d->F, d->WH.as<float>(), d->ldWH, d->A, d->ldA, e, s)));
@@ -128,9 +135,12 @@ int frob_numerator(evc_dict* d, const float* X, int ldX, int T, float* num0, int
 int objective_segments(evc_dict* d, const float* X, int ldX, int T, const float* H, int ldH, int loss, float eps,
                        const std::vector<int>& seg, std::vector<double>& err, cudaStream_t s) {
   EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, false, s));
-  simt::objective_rows_kernel<<<ceil_div(T, 8), 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, T, d->F, eps, loss,
-                                                            d->rowd.as<double>());
-  EVC_LAUNCH_CHECK();
+  {
+    ProfScope ps(3, s);
+    simt::objective_rows_kernel<<<ceil_div(T, 8), 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, T, d->F, eps, loss,
+                                                              d->rowd.as<double>());
+    EVC_LAUNCH_CHECK();
+  }
   EVC_CUDA(cudaMemcpyAsync(d->host_rows, d->rowd.p, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s));
   EVC_CUDA(cudaStreamSynchronize(s));
   const int nseg = (int)seg.size() - 1;
@@ -159,6 +169,7 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
     return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: max_iter/check_every/tol/lambda out of range");
   const float eps = p->epsilon > 0.f ? p->epsilon : kEpsilon;
   const int loss = p->loss;
+  g_prof = &d->prof;
   if (T == 0) {
     for (int u = 0; u < n_utt && res; ++u) res[u] = evc_solve_result{0, 0, 0.0, 0.0};
     return EVC_OK;
@@ -272,7 +283,8 @@ int evc_dict_destroy(evc_dict_t d) {
   cudaFree(d->A); cudaFree(d->B); cudaFree(d->colsum);
   d->tc_ops.release();
   d->WH.release(); d->R.release(); d->rowd.release(); d->w0.release(); d->active.release();
-  d->num0.release(); d->tcws.release();
+  d->num0.release(); d->tcws.release(); d->prof.release();
+  if (g_prof == &d->prof) g_prof = nullptr;
   if (d->host_rows) cudaFreeHost(d->host_rows);
   if (d->host_w0) cudaFreeHost(d->host_w0);
   if (d->host_active) cudaFreeHost(d->host_active);
@@ -369,6 +381,7 @@ static int product_impl(evc_dict_t d, const float* H, int ldH, int T, float* Y, 
   if (ldH < d->N || ldY < d->F) return fail(EVC_ERR_INVALID_ARGUMENT, "%s: ldH < N or ldY < F", who);
   if (T == 0) return EVC_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  g_prof = &d->prof;
   EVC_TRY(tc::check_alignment(d->mode, H, ldH));
   EVC_TRY(reserve_workspace(d, T, ldH, false));
   EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
@@ -391,6 +404,7 @@ int evc_objective(evc_dict_t d, const float* X, int ldX, int T, const float* H, 
   if (!d || !X || !H || !out || T < 1) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: bad argument");
   if (loss != EVC_LOSS_KL && loss != EVC_LOSS_FROBENIUS) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: bad loss");
   cudaStream_t s = (cudaStream_t)stream;
+  g_prof = &d->prof;
   EVC_TRY(reserve_workspace(d, T, ldH, false));
   EVC_TRY(tc::check_alignment(d->mode, H, ldH));
   EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
@@ -459,6 +473,28 @@ int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total) {
   if (c && n_total < d->N) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_attach_comm: n_total < local N");
   d->comm = c;
   d->n_total = c ? n_total : d->N;
+  return EVC_OK;
+}
+
+int evc_profile_enable(evc_dict_t d, int on) {
+  if (!d) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_profile_enable: null handle");
+  d->prof.on = on != 0;
+  d->prof.recs.clear();
+  d->prof.used = 0;
+  return EVC_OK;
+}
+
+int evc_profile_read(evc_dict_t d, double* ms, int* launches) {
+  if (!d || !ms || !launches) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_profile_read: null argument");
+  for (int c = 0; c < EVC_PROFILE_CLASSES; ++c) { ms[c] = 0.0; launches[c] = 0; }
+  if (d->prof.used) EVC_CUDA(cudaEventSynchronize(d->prof.ev[d->prof.used - 1]));
+  for (const Profiler::Rec& r : d->prof.recs) {
+    float t = 0.f;
+    EVC_CUDA(cudaEventElapsedTime(&t, d->prof.ev[r.a], d->prof.ev[r.b]));
+    if (r.cls >= 0 && r.cls < EVC_PROFILE_CLASSES) { ms[r.cls] += t; launches[r.cls] += 1; }
+  }
+  d->prof.recs.clear();
+  d->prof.used = 0;
   return EVC_OK;
 }
 

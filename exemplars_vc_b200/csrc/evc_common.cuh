@@ -80,4 +80,33 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+
+// Optional per-kernel-class device timing (evc_profile_enable / evc_profile_read).
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  struct Rec { int cls; size_t a, b; };
+  std::vector<Rec> recs;
+  size_t mark(cudaStream_t s) {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    cudaEventRecord(ev[used], s);
+    return used++;
+  }
+  void release() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear(); recs.clear(); used = 0;
+  }
+};
+inline thread_local Profiler* g_prof = nullptr;
+struct ProfScope {
+  int cls; cudaStream_t s; size_t a = 0; bool on;
+  ProfScope(int c, cudaStream_t st) : cls(c), s(st), on(g_prof && g_prof->on) { if (on) a = g_prof->mark(s); }
+  ~ProfScope() { if (on) { size_t b = g_prof->mark(s); g_prof->recs.push_back({cls, a, b}); } }
+};
+
 }  // namespace evc

@@ -501,6 +501,7 @@ inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, i
   const C1Plan pl = plan_c1(o.F, o.N, T, bk);
   const size_t need = ws_partials_offset(o, mode, T, ldH) + (size_t)pl.splits * T * pl.ldp;
   EVC_TRY(ws->reserve(need * sizeof(float)));
+  ProfScope ps(3, s);
   if (mode == EVC_MODE_3XTF32) EVC_TRY(launch_split_lo(H, ws->as<float>(), (size_t)T * ldH, s));
   return EVC_OK;
 }
@@ -521,8 +522,12 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   p.num_m_groups = pl.m_groups; p.num_t_tiles = pl.t_tiles; p.num_splits = pl.splits;
   p.kblocks_per_split = pl.kb_per_split; p.kblocks_total = pl.kb_total;
   p.out = partials; p.ld_out = pl.ldp;
-  EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL>(target ? o.tmBT : o.tmAT, target ? o.tmBT_lo : o.tmAT_lo,
-                                                                    tmH, tmHlo, p, s)));
+  {
+    ProfScope ps(0, s);
+    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL>(target ? o.tmBT : o.tmAT,
+                                                                      target ? o.tmBT_lo : o.tmAT_lo, tmH, tmHlo, p, s)));
+  }
+  ProfScope ps(1, s);
   dim3 g(T, ceil_div(ldWH, 128));
   reduce_partials_kernel<<<g, 128, 0, s>>>(partials, pl.splits, T, pl.ldp, o.F, WH, ldWH);
   EVC_LAUNCH_CHECK();
@@ -547,11 +552,13 @@ inline int contract2_t(DictOperands& o, int T, const float* R, const float* R_lo
   p.M_total = o.N; p.T = T; p.K = o.F;
   p.num_m_groups = ceil_div(o.N, 128 * kC2MTiles); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(o.F, bk); p.kblocks_per_split = p.kblocks_total;
+  ProfScope ps(2, s);
   return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi>(o.tmA, o.tmA_lo, tmR, tmRlo, p, s);
 }
 
 inline int launch_ratio(const float* X, int ldX, const float* WH, int ldWH, float* R, float* R_lo, int ldR, int T, int F,
                         float eps, int copy, cudaStream_t s) {
+  ProfScope ps(1, s);
   dim3 g(T, ceil_div(ldR, 128));
   ratio_split_kernel<<<g, 128, 0, s>>>(X, ldX, WH, ldWH, R, R_lo, ldR, T, F, eps, copy);
   EVC_LAUNCH_CHECK();

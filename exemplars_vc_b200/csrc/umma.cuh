@@ -3,6 +3,7 @@
 // Hand-written inline PTX; the field layouts follow the PTX ISA tcgen05 descriptor tables.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -32,8 +33,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Blocking wait with a watchdog: a wait that lasts ~2 s of SM clock is a pipeline bug (wrong phase or a
+// missing arrive), never legitimate work; trap so the launch fails instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("evc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -244,6 +244,18 @@ class ExemplarDictionary:
                                   float(epsilon), C.byref(out), _stream(self.device)))
         return out.value
 
+    # -- diagnostics -----------------------------------------------------------------------------------
+    def profile(self, on: bool):
+        check(_lib.lib().evc_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """{class: (milliseconds, launches)} since the last read; classes as in include/evc.h."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int * 4)()
+        check(_lib.lib().evc_profile_read(self._h, ms, n))
+        names = ("contraction1", "reduce_ratio", "contraction2_update", "objective_init")
+        return {names[i]: (ms[i], n[i]) for i in range(4)}
+
     # -- host staging --------------------------------------------------------------------------------
     def to_host(self, t: torch.Tensor, key: Optional[str] = None) -> np.ndarray:
         """Device tensor -> numpy (the D2H leg of the end-to-end path).  With ``key`` the copy lands in a

@@ -159,6 +159,17 @@ int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total);
 /* Diagnostics: number of kernels this library has launched in this process. */
 long long evc_kernel_launch_count(void);
 
+/*
+ * Diagnostics: per-kernel-class device timing.  After evc_profile_enable(d, 1) every launch of the handle is
+ * bracketed by CUDA events on the caller's stream; evc_profile_read synchronises, sums the elapsed times per
+ * class, returns them and clears the log.  Classes: 0 = contraction 1 (A*H, B*H: tensor/FFMA GEMM),
+ * 1 = split-K reduction + ratio (memory-bound), 2 = contraction 2 with the fused multiplicative update,
+ * 3 = objective / init helpers.  ms[4] and launches[4] are host arrays.
+ */
+#define EVC_PROFILE_CLASSES 4
+int evc_profile_enable(evc_dict_t d, int on);
+int evc_profile_read(evc_dict_t d, double* ms, int* launches);
+
 #ifdef __cplusplus
 }
 #endif
