@@ -52,7 +52,8 @@ def test_frames_are_independent(dictionary, problem):
     lo, hi = 37, 101
     part = dictionary.solve(X[lo:hi], tol=0.0, max_iter=5, H0=H0[lo:hi]).H
     rel = float(torch.linalg.norm(part - full[lo:hi]) / torch.linalg.norm(part))
-    assert rel < (1e-5 if dictionary.mode != "tf32" else 1e-2), rel
+    # different T -> different split-K plan -> different accumulation chains in TMEM (accumulation)
+    assert rel < {"fp32": 1e-5, "3xtf32": 1e-4, "tf32": 1e-2}[dictionary.mode], rel
 
 
 def test_scale_equivariance(dictionary, problem):
@@ -97,11 +98,11 @@ def test_products_against_float64(dictionary, problem):
     y = dictionary.to_host(dictionary.convert(H)).astype(np.float64)
     ref = H.astype(np.float64) @ B.astype(np.float64)
     rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
-    assert rel < (2e-6 if dictionary.mode != "tf32" else 2e-3), rel
+    assert rel < {"fp32": 1e-5, "3xtf32": 1e-4, "tf32": 2e-3}[dictionary.mode], rel
     wh = dictionary.to_host(dictionary.reconstruct(H)).astype(np.float64)
     ref = H.astype(np.float64) @ A.astype(np.float64)
     rel = np.linalg.norm(wh - ref) / np.linalg.norm(ref)
-    assert rel < (2e-6 if dictionary.mode != "tf32" else 2e-3), rel
+    assert rel < {"fp32": 1e-5, "3xtf32": 1e-4, "tf32": 2e-3}[dictionary.mode], rel
 
 
 def test_oracle_crosscheck_full_dictionary(dictionary, problem):
