@@ -49,7 +49,7 @@ int reserve_workspace(evc_dict* d, int T, int ldH, bool need_num0) {
   d->ldWH = round_up(d->F, 4);
   d->ldR = tc::k_pitch(d->F);
   EVC_TRY(d->WH.reserve((size_t)T * d->ldWH * sizeof(float)));
-  EVC_TRY(d->R.reserve((size_t)T * d->ldR * sizeof(float) * 2));  // R and (3xTF32) its lo part
+  EVC_TRY(d->R.reserve((size_t)T * d->ldR * sizeof(float)));
   EVC_TRY(d->rowd.reserve((size_t)T * sizeof(double)));
   EVC_TRY(d->w0.reserve((size_t)T * sizeof(float)));
   EVC_TRY(d->active.reserve((size_t)T));
