@@ -20,6 +20,7 @@
 #include "evc_common.cuh"
 #include "umma.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace evc {
 namespace tc {
@@ -39,12 +40,14 @@ struct GemmParams {
   // fewer, longer K splits so every CTA carries the same number of MMAs.  items_main = work items of the
   // other groups; 0 splits_last means "no special last group".
   int items_main, splits_last, kblocks_per_split_last;
+  int m_fastest;  // work-item order: 1 = consecutive CTAs take consecutive dictionary-row groups of one frame tile
   float* out;    // PARTIAL: [split][t][m] with pitch ld_out;  MU_*: the activations H (T, ld_out)
   int ld_out;
   const float* colsum;
   const float* num0;  // MU_FRO: cached numerator X A^T, same pitch as H
   float lam, eps;
   const unsigned char* row_active;
+  int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops
 };
 
 struct WorkItem {
@@ -53,11 +56,18 @@ struct WorkItem {
 __device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item) {
   WorkItem w;
   if (item < p.items_main) {
-    w.t_tile = item % p.num_t_tiles;
-    const int rest = item / p.num_t_tiles;
     const int groups = p.splits_last ? p.num_m_groups - 1 : p.num_m_groups;
-    w.m_group = rest % groups;
-    w.split = rest / groups;
+    if (p.m_fastest) {
+      w.m_group = item % groups;
+      const int rest = item / groups;
+      w.t_tile = rest % p.num_t_tiles;
+      w.split = rest / p.num_t_tiles;
+    } else {
+      w.t_tile = item % p.num_t_tiles;
+      const int rest = item / p.num_t_tiles;
+      w.m_group = rest % groups;
+      w.split = rest / groups;
+    }
     w.kb0 = w.split * p.kblocks_per_split;
     w.kb1 = min(w.kb0 + p.kblocks_per_split, p.kblocks_total);
   } else {
@@ -79,7 +89,12 @@ constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, interleaved 
 constexpr int kXformWarps = 4;  // dedicated hi/lo split warps (only when the epilogue overlaps the main loop)
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3>
+// The fused-update epilogue stages H through shared memory in [32 frames x 128 exemplars] chunks moved by TMA
+// (loads prefetched by a loader warp, stores issued by a storer warp): per-lane 128-byte global accesses
+// from the epilogue warps were limited by the SM's outstanding-miss capacity, bulk copies are not.
+constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = 4;
+
+template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, bool kStageH = false>
 struct TileCfg {
   static constexpr int kRowBytes = kBlockK * 4;
   static constexpr int kMTileBytes = 128 * kRowBytes;
@@ -91,7 +106,8 @@ struct TileCfg {
   static constexpr int kOffMlo = kMBytes;
   static constexpr int kOffN = kCopies * kMBytes;
   static constexpr int kOffNlo = kOffN + kNTileBytes;
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kHBytes = kStageH ? kHBufs * kHBufBytes : 0;
+  static constexpr int kStagesRaw = (kSmemBudget - kHBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccCols = kMTiles * kBlockT;
   static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
@@ -99,8 +115,12 @@ struct TileCfg {
   // hi/lo split needs its own warps; with one stage the (idle) epilogue warps do it.
   static constexpr bool kDedicatedXform = kSplit3 && kAccStages == 2;
   static constexpr int kXformThreads = kSplit3 ? (kDedicatedXform ? kXformWarps * 32 : kEpiWarps * 32) : 0;
-  static constexpr int kThreads = 64 + kEpiWarps * 32 + (kDedicatedXform ? kXformWarps * 32 : 0);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + slack to align the ring to 1024 B
+  static constexpr int kFirstXformWarp = 2 + kEpiWarps;
+  static constexpr int kLoaderWarp = kFirstXformWarp + (kDedicatedXform ? kXformWarps : 0);  // H chunk loader, then storer
+  static constexpr int kThreads = (kLoaderWarp + (kStageH ? 2 : 0)) * 32;
+  static constexpr int kOffH = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kHBytes + 1024;  // + slack to align the ring to 1024 B
+  static_assert(!kStageH || kMTiles == 1, "H staging assumes one 128-row sub-tile per work item");
   static_assert(kRowBytes == 64 || kRowBytes == 128, "K block must be one 64B or 128B swizzle row");
   static_assert(kStages >= 2, "tile does not fit twice in shared memory");
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
@@ -110,27 +130,33 @@ struct TileCfg {
 // lo = x - trunc_tf32(x) for one ring stage: element-wise on raw bytes, so the swizzled layout TMA wrote
 // carries over unchanged to the lo tiles.  `nthr` threads cooperate, 16 B per access (conflict-free).
 template <class Cfg>
-__device__ __forceinline__ void split_stage(uint8_t* stage, int tid, int nthr) {
-  const float4* mh = reinterpret_cast<const float4*>(stage);
-  float4* ml = reinterpret_cast<float4*>(stage + Cfg::kOffMlo);
-  const float4* nh = reinterpret_cast<const float4*>(stage + Cfg::kOffN);
-  float4* nl = reinterpret_cast<float4*>(stage + Cfg::kOffNlo);
-#pragma unroll 4
-  for (int q = tid; q < Cfg::kMBytes / 16; q += nthr) {
-    const float4 x = mh[q];
-    ml[q] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
-  }
-#pragma unroll 4
-  for (int q = tid; q < Cfg::kNTileBytes / 16; q += nthr) {
-    const float4 x = nh[q];
-    nl[q] = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
-  }
+__device__ __forceinline__ void split_stage(uint8_t* stage, int tid) {
+  constexpr int nthr = Cfg::kXformThreads > 0 ? Cfg::kXformThreads : 32;  // (1xTF32 instantiations never call this)
+  constexpr int kM = Cfg::kMBytes / 16 / nthr, kN = Cfg::kNTileBytes / 16 / nthr;
+  static_assert(Cfg::kMBytes % (16 * nthr) == 0 && Cfg::kNTileBytes % (16 * nthr) == 0, "split work must divide evenly");
+  const float4* mh = reinterpret_cast<const float4*>(stage) + tid;
+  float4* ml = reinterpret_cast<float4*>(stage + Cfg::kOffMlo) + tid;
+  const float4* nh = reinterpret_cast<const float4*>(stage + Cfg::kOffN) + tid;
+  float4* nl = reinterpret_cast<float4*>(stage + Cfg::kOffNlo) + tid;
+  float4 x[kM + kN];
+#pragma unroll
+  for (int q = 0; q < kM; ++q) x[q] = mh[q * nthr];
+#pragma unroll
+  for (int q = 0; q < kN; ++q) x[kM + q] = nh[q * nthr];
+#pragma unroll
+  for (int q = 0; q < kM; ++q)
+    ml[q * nthr] = make_float4(tf32_lo(x[q].x), tf32_lo(x[q].y), tf32_lo(x[q].z), tf32_lo(x[q].w));
+#pragma unroll
+  for (int q = 0; q < kN; ++q)
+    nl[q * nthr] = make_float4(tf32_lo(x[kM + q].x), tf32_lo(x[kM + q].y), tf32_lo(x[kM + q].z), tf32_lo(x[kM + q].w));
 }
 
 template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi>
-__global__ void __launch_bounds__((TileCfg<kMTiles, kBlockT, kBlockK, kSplit3>::kThreads), 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN, const GemmParams p) {
-  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3>;
+__global__ void __launch_bounds__((TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL>::kThreads), 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+               const __grid_constant__ CUtensorMap tmH, const GemmParams p) {
+  constexpr bool kStageH = (kEpi == TEPI_MU_KL);
+  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kStageH>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
   constexpr uint32_t kIdesc = make_idesc(kFmtTF32, 128, kBlockT);
@@ -141,6 +167,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_empty[kStages];  // MMAs that read the stage retired
   __shared__ __align__(8) uint64_t bar_acc_full[kAccStages];
   __shared__ __align__(8) uint64_t bar_acc_empty[kAccStages];
+  __shared__ __align__(8) uint64_t bar_hfull[kHBufs];   // H chunk landed in shared memory
+  __shared__ __align__(8) uint64_t bar_hready[kHBufs];  // the 4 epilogue warps of a chunk wrote the updated values
+  __shared__ __align__(8) uint64_t bar_hempty[kHBufs];  // the TMA store has read the buffer
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -151,6 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmM);
     tma_prefetch_desc(&tmN);
+    if (kStageH) tma_prefetch_desc(&tmH);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), 1);
       mbar_init(smem_u32(&bar_split[i]), Cfg::kXformThreads / 32);  // one elected lane per split warp
@@ -159,6 +189,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
       mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps);  // one elected lane of each epilogue warp
+    }
+    for (int i = 0; i < kHBufs; ++i) {
+      mbar_init(smem_u32(&bar_hfull[i]), 1);
+      mbar_init(smem_u32(&bar_hready[i]), 4);
+      mbar_init(smem_u32(&bar_hempty[i]), 1);
     }
     fence_barrier_init();
   }
@@ -185,6 +220,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
+          if (p.debug_flags & 4) {
+            mbar_arrive(full);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_arrive_expect_tx(full, (uint32_t)Cfg::kLoadBytes);
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
           const int kc = kb * kBlockK;
@@ -219,6 +259,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i) {
             if (m0 + i * 128 >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
+            if (p.debug_flags & 2) break;
             const uint32_t d = tmem_base + (uint32_t)((acc * kMTiles + i) * kBlockT);
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
@@ -243,17 +284,57 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
     }
-  } else if (warp >= 2 + kEpiWarps) {
+  } else if (kStageH && warp == Cfg::kLoaderWarp) {
+    // ================= H chunk loader: prefetches the activations the epilogue will update =================
+    if (lane == 0) {
+      int hbase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const WorkItem w = decode_item(p, item);
+        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * 128;
+        const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
+        for (int c = 0; c < nch; ++c) {
+          const int seq = hbase + c, b = seq % kHBufs;
+          const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
+          mbar_wait(smem_u32(&bar_hempty[b]), ph ^ 1u);
+          const uint32_t full = smem_u32(&bar_hfull[b]);
+          mbar_arrive_expect_tx(full, (uint32_t)kHBufBytes);
+          tma_load_2d(ring + Cfg::kOffH + b * kHBufBytes, &tmH, n0, t0 + c * kHChunkT, full, kEvictFirst);
+        }
+        hbase += nch;
+      }
+    }
+  } else if (kStageH && warp == Cfg::kLoaderWarp + 1) {
+    // ================= H chunk storer =================
+    if (lane == 0) {
+      int hbase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const WorkItem w = decode_item(p, item);
+        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * 128;
+        const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
+        for (int c = 0; c < nch; ++c) {
+          const int seq = hbase + c, b = seq % kHBufs;
+          const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
+          mbar_wait(smem_u32(&bar_hready[b]), ph);
+          tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * kHBufBytes);
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(smem_u32(&bar_hempty[b]));
+        }
+        hbase += nch;
+      }
+      tma_store_wait_all();
+    }
+  } else if (warp >= Cfg::kFirstXformWarp) {
     // ================= dedicated hi/lo split warps (3xTF32 with an overlapped epilogue) =================
     if (Cfg::kDedicatedXform) {
-      const int tid = threadIdx.x - (2 + kEpiWarps) * 32;
+      const int tid = threadIdx.x - Cfg::kFirstXformWarp * 32;
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const WorkItem w = decode_item(p, item);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
-          split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, tid, Cfg::kXformThreads);
+          if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, tid);
           fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_split[stage]));
@@ -267,7 +348,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     // the global-memory round trips of the fused update. =================
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    int acc = 0, stage = 0;
+    int acc = 0, stage = 0, hbase = 0;
     uint32_t acc_phase = 0, phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const WorkItem w = decode_item(p, item);
@@ -279,7 +360,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int tid = threadIdx.x - 64;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
-          split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, tid, Cfg::kXformThreads);
+          if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, tid);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_split[stage]));
@@ -288,8 +369,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       }
       mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
       tc_fence_after();
+      if (kStageH) {
+        // ---- fused multiplicative update through the shared-memory H chunks ----
+        const int m = m_group * 128 + quarter * 32 + lane;
+        float den = ((m < p.M_total) ? p.colsum[m] : 1.f) + p.lam;
+        if (den == 0.f) den = p.eps;
+        const float inv_den = __frcp_rn(den);
+        const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
+        for (int c = half; c < nch; c += 2) {
+          const int seq = hbase + c, b = seq % kHBufs;
+          const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockT + c * 32), v);
+          mbar_wait(smem_u32(&bar_hfull[b]), ph);
+          float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * kHBufBytes) + quarter * 32 + lane;
+          float h[32];
 #pragma unroll
-      for (int i = 0; i < kMTiles; ++i) {
+          for (int j = 0; j < 32; ++j) h[j] = hb[j * 128];
+          tmem_ld_wait();
+          if (p.row_active == nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
+          } else {
+            const int tb = t0 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (tb + j < p.T && p.row_active[tb + j]) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
+          }
+          if (!(p.debug_flags & 8)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hb[j * 128] = h[j];
+          }
+          fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_hready[b]));
+        }
+        hbase += nch;
+      }
+#pragma unroll
+      for (int i = 0; i < (kStageH ? 0 : kMTiles); ++i) {
         const int mrow0 = m_group * (128 * kMTiles) + i * 128;
         if (mrow0 >= p.M_total) break;  // whole sub-tile is padding (warp-uniform)
         const int m = mrow0 + quarter * 32 + lane;
@@ -300,15 +418,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           if (den == 0.f) den = p.eps;
           inv_den = __frcp_rn(den);
         }
+        // chunks of this warp: c = half, half+2, ...  The H values of the NEXT chunk are requested before the
+        // current one is processed (fast path), so a warp always has a full chunk of loads in flight.
+        const bool rows_full = (mrow0 + 128 <= p.M_total) && (p.row_active == nullptr);
+        float hn[32];
+        bool hn_valid = false;
+        if (kEpi != TEPI_PARTIAL) {
+          const int tb0 = t0 + half * 32;
+          if (rows_full && tb0 + 32 <= p.T) {
+            const float* o0 = p.out + (size_t)tb0 * p.ld_out + m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hn[j] = o0[(size_t)j * p.ld_out];
+            hn_valid = true;
+          }
+        }
         for (int c = half; c < kBlockT / 32; c += 2) {
           const int tb = t0 + c * 32;
           if (tb >= p.T) break;  // warp-uniform
+          if (p.debug_flags & 8) continue;
           uint32_t v[32];
           const uint32_t taddr =
               tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * kMTiles + i) * kBlockT + c * 32);
           tmem_ld_32x32(taddr, v);
           // whole chunk in range, every lane a real row, no frozen utterances: straight-line code
-          const bool fast = (tb + 32 <= p.T) && (mrow0 + 128 <= p.M_total) && (p.row_active == nullptr);
+          const bool fast = (tb + 32 <= p.T) && rows_full;
           if (kEpi == TEPI_PARTIAL) {
             tmem_ld_wait();
             float* o = p.out + ((size_t)split * p.T + tb) * p.ld_out + m;
@@ -321,12 +454,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                 if (m_ok && tb + j < p.T) o[(size_t)j * p.ld_out] = __uint_as_float(v[j]);
             }
           } else {
-            float h[32];
             float* o = p.out + (size_t)tb * p.ld_out + m;
             const float* q = (kEpi == TEPI_MU_FRO) ? p.num0 + (size_t)tb * p.ld_out + m : nullptr;
-            if (fast) {
+            if (fast && hn_valid) {
+              float h[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) h[j] = o[(size_t)j * p.ld_out];
+              for (int j = 0; j < 32; ++j) h[j] = hn[j];
+              // prefetch the next chunk of this warp
+              const int tbn = tb + 64;
+              hn_valid = (c + 2 < kBlockT / 32) && (tbn + 32 <= p.T);
+              if (hn_valid) {
+                const float* on = p.out + (size_t)tbn * p.ld_out + m;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hn[j] = on[(size_t)j * p.ld_out];
+              }
               tmem_ld_wait();
               if (kEpi == TEPI_MU_FRO) {
 #pragma unroll
@@ -342,6 +483,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) o[(size_t)j * p.ld_out] = h[j];
             } else {
+              hn_valid = false;
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -430,7 +572,8 @@ inline int get_encode(PFN_encodeTiled* out) {
 }
 
 // Row-major fp32 matrix (rows, cols) with pitch ld floats; box = box_rows x box_cols, box_cols*4 in {64,128}.
-inline int make_tmap(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+inline int make_tmap(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows,
+                     bool swizzle = true) {
   PFN_encodeTiled enc;
   EVC_TRY(get_encode(&enc));
   if (((uintptr_t)base & 15) || (ld & 3))
@@ -439,7 +582,8 @@ inline int make_tmap(CUtensorMap* m, const float* base, int rows, int cols, int 
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw = !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -475,8 +619,9 @@ inline int check_alignment(int mode, const float* H, int ldH) {
 }
 
 template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi>
-inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const GemmParams& p, cudaStream_t s) {
-  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3>;
+inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const GemmParams& p,
+                     cudaStream_t s) {
+  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL>;
   auto kern = tc_gemm_kernel<kMTiles, kBlockT, kBlockK, kSplit3, kEpi>;
   static bool configured = false;
   if (!configured) {
@@ -486,7 +631,10 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const GemmP
   const int items = p.items_main + p.splits_last * p.num_t_tiles;
   if (items <= 0) return EVC_OK;
   const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(tmM, tmN, p);
+  static const int dbg = getenv("EVC_DEBUG_FLAGS") ? atoi(getenv("EVC_DEBUG_FLAGS")) : 0;
+  GemmParams q = p;
+  q.debug_flags = dbg;
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(tmM, tmN, tmH, q);
   EVC_LAUNCH_CHECK();
   return EVC_OK;
 }
@@ -599,7 +747,7 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   p.out = partials; p.ld_out = pl.ldp;
   {
     ProfScope ps(0, s);
-    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL>(target ? o.tmBT : o.tmAT, tmH, p, s)));
+    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL>(target ? o.tmBT : o.tmAT, tmH, tmH, p, s)));
   }
   ProfScope ps(1, s);
   dim3 g(T, ceil_div(ldWH, 128));
@@ -625,8 +773,12 @@ inline int contract2_t(DictOperands& o, int T, const float* R, int ldR, GemmPara
   p.num_m_groups = ceil_div(o.N, 128 * kC2MTiles); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(o.F, bk); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
+  // neighbouring CTAs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
+  p.m_fastest = getenv("EVC_T_FASTEST") ? 0 : 1;
+  CUtensorMap tmHc = tmR;  // only the fused KL update stages H through shared memory
+  if (kEpi == TEPI_MU_KL) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
   ProfScope ps(2, s);
-  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi>(o.tmA, tmR, p, s);
+  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi>(o.tmA, tmR, tmHc, p, s);
 }
 
 inline int launch_ratio(const float* X, int ldX, const float* WH, int ldWH, float* R, int ldR, int T, int F,
