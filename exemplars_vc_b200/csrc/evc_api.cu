@@ -70,14 +70,15 @@ int reserve_workspace(evc_dict* d, int T, int ldH, bool need_num0) {
 // ---- the three contractions, dispatched on mode -------------------------------------------------
 
 // WH (T, ldWH) = H (T,N) * A (N,F)         [first contraction; sklearn :554]
-int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH, bool target, cudaStream_t s) {
+int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH, bool target, cudaStream_t s,
+                const tc::RatioArgs* ra = nullptr) {
   if (d->mode == EVC_MODE_FP32) {
     ProfScope ps(0, s);
     simt::EpiArgs e{};
     e.C = WH; e.ldc = ldWH;
     EVC_TRY((simt::launch_gemm<simt::EPI_STORE, false>(T, d->F, d->N, H, ldH, target ? d->B : d->A, d->ldA, e, s)));
   } else {
-    EVC_TRY(tc::contract_wh(d->tc_ops, d->mode, H, ldH, T, WH, ldWH, target, &d->tcws, s));
+    EVC_TRY(tc::contract_wh(d->tc_ops, d->mode, H, ldH, T, WH, ldWH, target, &d->tcws, s, ra));
   }
   if (d->comm && d->comm->world > 1) {
     EVC_TRY(nccl::all_reduce_sum(d->comm->comm, WH, (size_t)T * ldWH, s));
@@ -87,7 +88,7 @@ int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH
 
 // KL: H *= (R A^T) / (A^T1 + lam)   [second contraction + multiplicative update; sklearn :585-624]
 int update_kl(evc_dict* d, const float* X, int ldX, int T, float* H, int ldH, float lam, float eps,
-              const unsigned char* row_active, cudaStream_t s) {
+              const unsigned char* row_active, cudaStream_t s, bool ratio_done = false) {
   float* R = d->R.as<float>();
   if (d->mode == EVC_MODE_FP32) {
     {
@@ -103,7 +104,7 @@ int update_kl(evc_dict* d, const float* X, int ldX, int T, float* H, int ldH, fl
     return EVC_OK;
   }
   return tc::update_kl(d->tc_ops, d->mode, X, ldX, T, d->WH.as<float>(), d->ldWH, R, d->ldR, H, ldH, d->colsum,
-                       lam, eps, row_active, &d->tcws, s);
+                       lam, eps, row_active, &d->tcws, s, ratio_done);
 }
 
 // Frobenius: H *= NUM0 / (WH A^T + lam)   [sklearn :535-549, with A^T(A H) instead of the N x N Gram]
@@ -217,15 +218,25 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
   float* num0 = d->num0.as<float>();
   if (loss == EVC_LOSS_FROBENIUS) EVC_TRY(frob_numerator(d, X, ldX, T, num0, ldH, s));
 
+  // tensor-core modes on one GPU: the split-K reduction of contraction 1 emits the ratio in the same pass
+  const bool fuse_ratio = d->mode != EVC_MODE_FP32 && loss == EVC_LOSS_KL && !(d->comm && d->comm->world > 1);
+  const tc::RatioArgs ra{X, ldX, d->R.as<float>(), d->ldR, eps};
+  bool wh_fresh = true;  // WH = H A of the current H is in the workspace (the objective at init just made it)
   for (int k = 1; k <= p->max_iter && n_active > 0; ++k) {
     const float lam = p->lambda + (float)k * p->lambda_step;
     const unsigned char* mask = any_frozen ? d->active.as<unsigned char>() : nullptr;
-    EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, false, s));
-    if (loss == EVC_LOSS_KL) EVC_TRY(update_kl(d, X, ldX, T, H, ldH, lam, eps, mask, s));
+    bool ratio_done = false;
+    if (!wh_fresh) {
+      EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, false, s, fuse_ratio ? &ra : nullptr));
+      ratio_done = fuse_ratio;
+    }
+    wh_fresh = false;
+    if (loss == EVC_LOSS_KL) EVC_TRY(update_kl(d, X, ldX, T, H, ldH, lam, eps, mask, s, ratio_done));
     else EVC_TRY(update_fro(d, T, H, ldH, num0, lam, eps, mask, s));
 
     if (p->tol > 0.f && k % p->check_every == 0) {  // sklearn :867-879
       EVC_TRY(objective_segments(d, X, ldX, T, H, ldH, loss, eps, seg, err, s));
+      wh_fresh = true;  // the next iteration reuses this A*H (sklearn recomputes it, _nmf.py:554 after :868)
       bool changed = false;
       for (int u = 0; u < nseg; ++u) {
         if (!active[u]) continue;

@@ -47,8 +47,29 @@ struct GemmParams {
   const float* num0;  // MU_FRO: cached numerator X A^T, same pitch as H
   float lam, eps;
   const unsigned char* row_active;
+  // Dictionary rows F_main..F-1 that contraction 1 does not run through the tensor cores (F = 513 = 4*128 + 1):
+  // the fused update accumulates their share of the NEXT A*H, sum_n h_new[t,n] * A[n, F_main+l], per warp.
+  const float* left_a;  // (n_left, left_lda): rows F_main.. of the transposed dictionary (contiguous in n)
+  int left_lda, n_left;
+  float* left_out;      // [(m_group*4 + quarter)][l][t] partial sums, pitch left_ld
+  int left_ld;
   int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops
 };
+
+// vals[j] (j = 0..31) per lane -> returns, in lane L, the sum over all 32 lanes of vals[L]  (31 shuffles).
+__device__ __forceinline__ float warp_transpose_sum(float (&vals)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? vals[i] : vals[i + off];
+      const float keep = up ? vals[i + off] : vals[i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return vals[0];
+}
 
 struct WorkItem {
   int m_group, t_tile, split, kb0, kb1;
@@ -403,6 +424,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA store
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_hready[b]));
+          for (int l = 0; l < p.n_left; ++l) {
+            // (rows past T and exemplars past N were zero-filled by TMA: they add nothing)
+            const float a = (m < p.M_total) ? p.left_a[(size_t)l * p.left_lda + m] : 0.f;
+            float sv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sv[j] = h[j] * a;
+            const float tot = warp_transpose_sum(sv, lane);
+            p.left_out[((size_t)(m_group * 4 + quarter) * p.n_left + l) * p.left_ld + (t0 + c * 32 + lane)] = tot;
+          }
         }
         hbase += nch;
       }
@@ -522,18 +552,81 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 
 // ---- memory-bound helpers ------------------------------------------------------------------------
 
-// WH[t,f] = sum_s P[s][t][f]   (fixed order: deterministic)
+// WH[t,f] = sum_s P[s][t][f] for the tensor-core rows f < F_main (fixed order: deterministic);
+// WH[t,F_main+l] = sum_r L[r][l][t] from the fused update's per-warp partials when `left_rows` > 0.
+// With `R` != nullptr it also emits the ratio R = X / max(WH, eps) (zero pad columns) in the same pass.
 __global__ void reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp,
-                                       int F, float* __restrict__ WH, int ldwh) {
+                                       int F, int F_main, float* __restrict__ WH, int ldwh,
+                                       const float* __restrict__ L, int left_rows, int n_left, int left_ld,
+                                       const float* __restrict__ X, int ldx, float* __restrict__ R, int ldr, float eps) {
   const int f = blockIdx.y * blockDim.x + threadIdx.x;
   const int t = blockIdx.x;
-  if (t >= T || f >= ldwh) return;
+  if (t >= T) return;
   float s = 0.f;
-  if (f < F) {
+  bool have = false;
+  if (f < F_main) {
     const int n = (f >= f_last) ? S_last : S;  // columns of the last row group have their own split count
     for (int k = 0; k < n; ++k) s += P[((size_t)k * T + t) * ldp + f];
+    have = true;
+  } else if (f < F && left_rows > 0) {
+    const int l = f - F_main;
+    for (int r = 0; r < left_rows; ++r) s += L[((size_t)r * n_left + l) * left_ld + t];
+    have = true;
   }
-  WH[(size_t)t * ldwh + f] = s;
+  if (f < ldwh && (have || f >= F)) WH[(size_t)t * ldwh + f] = s;
+  if (R && f < ldr) R[(size_t)t * ldr + f] = (have && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s, eps)) : 0.f;
+}
+
+// Collapse the fused update's per-warp leftover partials L[r][l][t] (r = m_group*4 + quarter) to one row per
+// leftover column: out[l][t] = sum_r L[r][l][t].  Block = 32 frames x 32 row groups, fixed order (deterministic).
+__global__ void __launch_bounds__(1024)
+left_reduce_kernel(const float* __restrict__ L, int rows, int n_left, int ld, int T, float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int t = blockIdx.x * 32 + tx, l = blockIdx.y;
+  float acc = 0.f;
+  if (t < T)
+    for (int r = ty; r < rows; r += 32) acc += L[((size_t)r * n_left + l) * ld + t];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && t < T) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v += red[k][tx];
+    out[(size_t)l * ld + t] = v;
+  }
+}
+
+// Standalone leftover rows: WH[t, F_main+l] = sum_n H[t,n] * a[l][n].  One block per frame; used whenever the
+// fused update has not just produced the partials (first iteration, objective of a given H, conversion).
+__global__ void __launch_bounds__(256)
+leftover_rows_kernel(const float* __restrict__ H, int ldh, int T, int N, const float* __restrict__ a, int lda,
+                     int n_left, float* __restrict__ WH, int ldwh, int F_main) {
+  __shared__ float red[8][8];
+  const int t = blockIdx.x;
+  float acc[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float h = H[(size_t)t * ldh + n];
+#pragma unroll
+    for (int l = 0; l < 8; ++l)
+      if (l < n_left) acc[l] = fmaf(h, a[(size_t)l * lda + n], acc[l]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) {
+    float v = acc[l];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][l] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_left) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    WH[(size_t)t * ldwh + F_main + threadIdx.x] = v;
+  }
 }
 
 // R = X / max(WH, eps) with zeroed pad columns; `copy` = 1 stores WH itself (Frobenius: the second
@@ -654,6 +747,8 @@ struct DictOperands {
   float* AT = nullptr;       // (F, ldN) transposed copy: K-major operand of contraction 1
   float* BT = nullptr;       // (F, ldN) transposed target dictionary: operand of the conversion
   CUtensorMap tmA, tmAT, tmBT;
+  int F_main = 0, n_left = 0;  // contraction 1 runs rows [0, F_main) on the tensor cores; n_left = F - F_main <= 8
+  bool left_valid = false;     // the workspace holds leftover partials of the CURRENT activations
   void release() {
     cudaFree(AT); cudaFree(BT);
     AT = BT = nullptr;
@@ -664,6 +759,10 @@ inline int build_operands(DictOperands* o, int mode, const float* A, const float
   if (mode == EVC_MODE_BF16) return fail(EVC_ERR_UNSUPPORTED, "EVC_MODE_BF16 is not implemented yet");
   const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
   o->F = F; o->N = N; o->ldA = ldA; o->ldN = round_up(N, 4); o->A = A; o->has_target = (B != nullptr);
+  // A few rows past a multiple of 128 (the Nyquist bin of a 513-bin spectrum) would cost a whole 128-row MMA
+  // tile; they are handled as dot products on the CUDA cores instead.
+  o->n_left = (F > 128 && (F % 128) <= 8 && !getenv("EVC_NO_LEFTOVER")) ? F % 128 : 0;
+  o->F_main = F - o->n_left;
   const size_t at_bytes = (size_t)F * o->ldN * sizeof(float);
   dim3 tb(32, 8), tg(ceil_div(N, 32), ceil_div(F, 32));
   EVC_CUDA(cudaMalloc(&o->AT, at_bytes));
@@ -671,13 +770,13 @@ inline int build_operands(DictOperands* o, int mode, const float* A, const float
   simt::transpose_kernel<<<tg, tb, 0, s>>>(A, ldA, o->AT, o->ldN, N, F);
   EVC_LAUNCH_CHECK();
   EVC_TRY(make_tmap(&o->tmA, A, N, F, ldA, bk, 128));
-  EVC_TRY(make_tmap(&o->tmAT, o->AT, F, N, o->ldN, bk, 128));
+  EVC_TRY(make_tmap(&o->tmAT, o->AT, o->F_main, N, o->ldN, bk, 128));
   if (B) {
     EVC_CUDA(cudaMalloc(&o->BT, at_bytes));
     EVC_CUDA(cudaMemsetAsync(o->BT, 0, at_bytes, s));
     simt::transpose_kernel<<<tg, tb, 0, s>>>(B, ldA, o->BT, o->ldN, N, F);
     EVC_LAUNCH_CHECK();
-    EVC_TRY(make_tmap(&o->tmBT, o->BT, F, N, o->ldN, bk, 128));
+    EVC_TRY(make_tmap(&o->tmBT, o->BT, o->F_main, N, o->ldN, bk, 128));
   }
   return EVC_OK;
 }
@@ -723,23 +822,44 @@ inline C1Plan plan_c1(int F, int N, int T, int bk) {
 }
 
 // Called before a solve / product: make sure the workspace can hold the split-K partials.
+// Workspace layout: [ split-K partials | leftover-row partials of the fused update ].
+inline size_t ws_left_offset(const C1Plan& pl, int T) { return round_up_sz((size_t)pl.max_splits * T * pl.ldp, 64); }
+inline int left_rows(const DictOperands& o) { return ceil_div(o.N, 128) * 4; }
+inline int left_ld(int T) { return round_up(T, kC2BlockT); }
+
 inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, int T, DevBuf* ws, cudaStream_t s) {
   if (mode == EVC_MODE_FP32) return EVC_OK;
   const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
-  const C1Plan pl = plan_c1(o.F, o.N, T, bk);
-  return ws->reserve((size_t)pl.max_splits * T * pl.ldp * sizeof(float));
+  const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
+  o.left_valid = false;
+  const size_t left = (size_t)(left_rows(o) + 1) * o.n_left * left_ld(T);  // per-warp partials + their sum
+  return ws->reserve((ws_left_offset(pl, T) + left) * sizeof(float));
+}
+
+struct RatioArgs {  // fuse R = X / max(WH, eps) into the split-K reduction
+  const float* X; int ldX; float* R; int ldR; float eps;
+};
+
+inline int launch_ratio(const float* X, int ldX, const float* WH, int ldWH, float* R, int ldR, int T, int F,
+                        float eps, int copy, cudaStream_t s) {
+  ProfScope ps(1, s);
+  dim3 g(T, ceil_div(ldR, 128));
+  ratio_pad_kernel<<<g, 128, 0, s>>>(X, ldX, WH, ldWH, R, ldR, T, F, eps, copy);
+  EVC_LAUNCH_CHECK();
+  return EVC_OK;
 }
 
 template <bool kSplit3>
 inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
-                         DevBuf* ws, cudaStream_t s) {
+                         DevBuf* ws, cudaStream_t s, const RatioArgs* ra) {
   constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;
-  const C1Plan pl = plan_c1(o.F, o.N, T, bk);
+  const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
   float* partials = ws->as<float>();
+  float* leftp = ws->as<float>() + ws_left_offset(pl, T);
   CUtensorMap tmH;
   EVC_TRY(make_tmap(&tmH, H, T, o.N, ldH, bk, kC1BlockT));
   GemmParams p{};
-  p.M_total = o.F; p.T = T; p.K = o.N;
+  p.M_total = o.F_main; p.T = T; p.K = o.N;
   p.num_m_groups = pl.m_groups; p.num_t_tiles = pl.t_tiles; p.num_splits = pl.splits;
   p.kblocks_per_split = pl.kb_per_split; p.kblocks_total = pl.kb_total;
   p.splits_last = pl.splits_last; p.kblocks_per_split_last = pl.kb_per_split_last;
@@ -749,18 +869,40 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
     ProfScope ps(0, s);
     EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL>(target ? o.tmBT : o.tmAT, tmH, tmH, p, s)));
   }
-  ProfScope ps(1, s);
-  dim3 g(T, ceil_div(ldWH, 128));
-  reduce_partials_kernel<<<g, 128, 0, s>>>(partials, pl.splits, pl.splits_last, pl.f_last, T, pl.ldp, o.F, WH, ldWH);
-  EVC_LAUNCH_CHECK();
+  // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
+  const bool from_partials = o.n_left > 0 && !target && o.left_valid;
+  const bool standalone = o.n_left > 0 && !from_partials;
+  {
+    ProfScope ps(1, s);
+    float* leftsum = leftp + (size_t)left_rows(o) * o.n_left * left_ld(T);
+    if (from_partials) {
+      dim3 lg(ceil_div(T, 32), o.n_left), lb(32, 32);
+      left_reduce_kernel<<<lg, lb, 0, s>>>(leftp, left_rows(o), o.n_left, left_ld(T), T, leftsum);
+      EVC_LAUNCH_CHECK();
+    }
+    const int cols = std::max(ldWH, ra ? ra->ldR : 0);
+    dim3 g(T, ceil_div(cols, 128));
+    const bool fuse = ra && !standalone;
+    reduce_partials_kernel<<<g, 128, 0, s>>>(partials, pl.splits, pl.splits_last, pl.f_last, T, pl.ldp, o.F, o.F_main, WH,
+                                             ldWH, leftsum, from_partials ? 1 : 0, o.n_left, left_ld(T),
+                                             fuse ? ra->X : nullptr, fuse ? ra->ldX : 0, fuse ? ra->R : nullptr,
+                                             fuse ? ra->ldR : 0, fuse ? ra->eps : 0.f);
+    EVC_LAUNCH_CHECK();
+    if (standalone) {
+      const float* rows = (target ? o.BT : o.AT) + (size_t)o.F_main * o.ldN;
+      leftover_rows_kernel<<<T, 256, 0, s>>>(H, ldH, T, o.N, rows, o.ldN, o.n_left, WH, ldWH, o.F_main);
+      EVC_LAUNCH_CHECK();
+    }
+  }
+  if (ra && standalone) EVC_TRY(launch_ratio(ra->X, ra->ldX, WH, ldWH, ra->R, ra->ldR, T, o.F, ra->eps, 0, s));
   return EVC_OK;
 }
 
 inline int contract_wh(DictOperands& o, int mode, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
-                       DevBuf* ws, cudaStream_t s) {
+                       DevBuf* ws, cudaStream_t s, const RatioArgs* ra = nullptr) {
   if (target && !o.has_target) return fail(EVC_ERR_INVALID_ARGUMENT, "no target dictionary");
-  if (mode == EVC_MODE_3XTF32) return contract_wh_t<true>(o, H, ldH, T, WH, ldWH, target, ws, s);
-  return contract_wh_t<false>(o, H, ldH, T, WH, ldWH, target, ws, s);
+  if (mode == EVC_MODE_3XTF32) return contract_wh_t<true>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  return contract_wh_t<false>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
 }
 
 // Second contraction with a fused epilogue.  `R` is what multiplies A^T: the ratio (KL) or A H (Frobenius).
@@ -781,22 +923,20 @@ inline int contract2_t(DictOperands& o, int T, const float* R, int ldR, GemmPara
   return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi>(o.tmA, tmR, tmHc, p, s);
 }
 
-inline int launch_ratio(const float* X, int ldX, const float* WH, int ldWH, float* R, int ldR, int T, int F,
-                        float eps, int copy, cudaStream_t s) {
-  ProfScope ps(1, s);
-  dim3 g(T, ceil_div(ldR, 128));
-  ratio_pad_kernel<<<g, 128, 0, s>>>(X, ldX, WH, ldWH, R, ldR, T, F, eps, copy);
-  EVC_LAUNCH_CHECK();
-  return EVC_OK;
-}
-
 inline int update_kl(DictOperands& o, int mode, const float* X, int ldX, int T, const float* WH, int ldWH, float* R,
                      int ldR, float* H, int ldH, const float* colsum, float lam, float eps,
-                     const unsigned char* row_active, DevBuf* ws, cudaStream_t s) {
-  EVC_TRY(launch_ratio(X, ldX, WH, ldWH, R, ldR, T, o.F, eps, 0, s));
+                     const unsigned char* row_active, DevBuf* ws, cudaStream_t s, bool ratio_done = false) {
+  if (!ratio_done) EVC_TRY(launch_ratio(X, ldX, WH, ldWH, R, ldR, T, o.F, eps, 0, s));
   GemmParams p{};
   p.out = H; p.ld_out = ldH;
   p.colsum = colsum; p.lam = lam; p.eps = eps; p.row_active = row_active;
+  if (o.n_left > 0) {
+    const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
+    const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
+    p.left_a = o.AT + (size_t)o.F_main * o.ldN; p.left_lda = o.ldN; p.n_left = o.n_left;
+    p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T);
+    o.left_valid = true;  // (stream order: the partials are complete before the next contraction 1 reads them)
+  }
   if (mode == EVC_MODE_3XTF32) return contract2_t<true, TEPI_MU_KL>(o, T, R, ldR, p, s);
   return contract2_t<false, TEPI_MU_KL>(o, T, R, ldR, p, s);
 }
@@ -805,6 +945,7 @@ inline int update_fro(DictOperands& o, int mode, int T, const float* WH, int ldW
                       const float* num0, float lam, float eps, const unsigned char* row_active, DevBuf* ws,
                       cudaStream_t s) {
   EVC_TRY(launch_ratio(nullptr, 0, WH, ldWH, R, ldR, T, o.F, eps, 1, s));
+  o.left_valid = false;
   GemmParams p{};
   p.out = H; p.ld_out = ldH;
   p.num0 = num0; p.lam = lam; p.eps = eps; p.row_active = row_active;
