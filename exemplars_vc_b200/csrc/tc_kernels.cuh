@@ -53,7 +53,8 @@ struct GemmParams {
   int left_lda, n_left;
   float* left_out;      // [(m_group*4 + quarter)][l][t] partial sums, pitch left_ld
   int left_ld;
-  int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops
+  long long* dbg_cycles;  // EVC_DEBUG_TIMING: per-CTA [8] cycle counters of the role threads (nullptr = off)
+  int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops, 16 no L2 look-ahead prefetch
 };
 
 // vals[j] (j = 0..31) per lane -> returns, in lane L, the sum over all 32 lanes of vals[L]  (31 shuffles).
@@ -115,15 +116,20 @@ constexpr int kSmemBudget = 227 * 1024 - 2048;
 // from the epilogue warps were limited by the SM's outstanding-miss capacity, bulk copies are not.
 constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = 4;
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, bool kStageH = false>
+// kCG = CTA group size of the MMA.  1: one SM per tile.  2: a CTA pair (cluster of 2) shares each tile --
+// tcgen05.mma.cta_group::2 with M = 256 (128 dictionary rows per CTA) and the frame (N) operand split in halves
+// between the two CTAs' shared memories, which halves the per-SM shared-memory reads of the frame operand
+// (the 3xTF32 main loop of the 1-CTA version is shared-memory-bandwidth bound).
+template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, bool kStageH, int kCG>
 struct TileCfg {
   static constexpr int kRowBytes = kBlockK * 4;
-  static constexpr int kMTileBytes = 128 * kRowBytes;
-  static constexpr int kNTileBytes = kBlockT * kRowBytes;
+  static constexpr int kMTileBytes = 128 * kRowBytes;              // this CTA's 128 rows of one dictionary sub-tile
+  static constexpr int kNRows = kBlockT / kCG;                     // frame rows this CTA loads
+  static constexpr int kNTileBytes = kNRows * kRowBytes;
   static constexpr int kCopies = kSplit3 ? 2 : 1;
-  static constexpr int kMBytes = kMTiles * kMTileBytes;                // hi tiles of the dictionary operand
-  static constexpr int kLoadBytes = kMBytes + kNTileBytes;             // what TMA brings per stage (hi only)
-  static constexpr int kStageBytes = kCopies * kLoadBytes;             // + the lo tiles computed in place
+  static constexpr int kMBytes = kMTiles * kMTileBytes;            // hi tiles of the dictionary operand
+  static constexpr int kLoadBytes = kMBytes + kNTileBytes;         // what TMA brings per stage (hi only)
+  static constexpr int kStageBytes = kCopies * kLoadBytes;         // + the lo tiles computed in place
   static constexpr int kOffMlo = kMBytes;
   static constexpr int kOffN = kCopies * kMBytes;
   static constexpr int kOffNlo = kOffN + kNTileBytes;
@@ -136,58 +142,71 @@ struct TileCfg {
   // hi/lo split needs its own warps; with one stage the (idle) epilogue warps do it.
   static constexpr bool kDedicatedXform = kSplit3 && kAccStages == 2;
   static constexpr int kXformThreads = kSplit3 ? (kDedicatedXform ? kXformWarps * 32 : kEpiWarps * 32) : 0;
+  // A pair without split warps still needs someone to tell the leader that the peer's TMA bytes landed.
+  static constexpr bool kRelay = (kCG == 2) && !kSplit3;
+  // arrivals per CTA on the leader's "stage ready" barrier
+  static constexpr int kReadyArrivals = 1;  // the warp that owns the stage (split warps take K-blocks round-robin)
+  static constexpr int kSplitWarps = kXformThreads > 0 ? kXformThreads / 32 : 1;
   static constexpr int kFirstXformWarp = 2 + kEpiWarps;
-  static constexpr int kLoaderWarp = kFirstXformWarp + (kDedicatedXform ? kXformWarps : 0);  // H chunk loader, then storer
+  static constexpr int kRelayWarp = kFirstXformWarp + (kDedicatedXform ? kXformWarps : 0);
+  static constexpr int kLoaderWarp = kRelayWarp + (kRelay ? 1 : 0);  // H chunk loader, then storer
   static constexpr int kThreads = (kLoaderWarp + (kStageH ? 2 : 0)) * 32;
   static constexpr int kOffH = kStages * kStageBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kHBytes + 1024;  // + slack to align the ring to 1024 B
-  static_assert(!kStageH || kMTiles == 1, "H staging assumes one 128-row sub-tile per work item");
+  static constexpr int kRowsPerSub = 128 * kCG;                   // dictionary rows of one MMA (M = 128 or 256)
   static_assert(kRowBytes == 64 || kRowBytes == 128, "K block must be one 64B or 128B swizzle row");
   static_assert(kStages >= 2, "tile does not fit twice in shared memory");
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
   static_assert(kBlockT % 32 == 0 && kBlockT >= 32 && kBlockT <= 256, "bad frame tile");
+  static_assert(!kStageH || kMTiles == 1, "H staging assumes one sub-tile per work item");
+  static_assert(kCG == 1 || kCG == 2, "CTA group is 1 or 2");
 };
 
 // lo = x - trunc_tf32(x) for one ring stage: element-wise on raw bytes, so the swizzled layout TMA wrote
-// carries over unchanged to the lo tiles.  `nthr` threads cooperate, 16 B per access (conflict-free).
+// carries over unchanged to the lo tiles.  ONE warp owns a whole stage (the split warps take K-blocks
+// round-robin): the per-stage cost is dominated by fixed latencies (barrier wake-up, proxy fence, arrive),
+// so several stages are split concurrently instead of all warps sharing one.  16 B per lane per access,
+// batches of 8 loads in flight.
 template <class Cfg>
-__device__ __forceinline__ void split_stage(uint8_t* stage, int tid) {
-  constexpr int nthr = Cfg::kXformThreads > 0 ? Cfg::kXformThreads : 32;  // (1xTF32 instantiations never call this)
-  constexpr int kM = Cfg::kMBytes / 16 / nthr, kN = Cfg::kNTileBytes / 16 / nthr;
-  static_assert(Cfg::kMBytes % (16 * nthr) == 0 && Cfg::kNTileBytes % (16 * nthr) == 0, "split work must divide evenly");
-  const float4* mh = reinterpret_cast<const float4*>(stage) + tid;
-  float4* ml = reinterpret_cast<float4*>(stage + Cfg::kOffMlo) + tid;
-  const float4* nh = reinterpret_cast<const float4*>(stage + Cfg::kOffN) + tid;
-  float4* nl = reinterpret_cast<float4*>(stage + Cfg::kOffNlo) + tid;
-  float4 x[kM + kN];
+__device__ __forceinline__ void split_region(const uint8_t* hi, uint8_t* lo, int bytes, int lane) {
+  const float4* src = reinterpret_cast<const float4*>(hi) + lane;
+  float4* dst = reinterpret_cast<float4*>(lo) + lane;
+  const int n = bytes / 16 / 32;  // float4 per lane (a multiple of 8: tiles are >= 4 KB)
+  for (int q0 = 0; q0 < n; q0 += 8) {
+    float4 x[8];
 #pragma unroll
-  for (int q = 0; q < kM; ++q) x[q] = mh[q * nthr];
+    for (int q = 0; q < 8; ++q) x[q] = src[(q0 + q) * 32];
 #pragma unroll
-  for (int q = 0; q < kN; ++q) x[kM + q] = nh[q * nthr];
-#pragma unroll
-  for (int q = 0; q < kM; ++q)
-    ml[q * nthr] = make_float4(tf32_lo(x[q].x), tf32_lo(x[q].y), tf32_lo(x[q].z), tf32_lo(x[q].w));
-#pragma unroll
-  for (int q = 0; q < kN; ++q)
-    nl[q * nthr] = make_float4(tf32_lo(x[kM + q].x), tf32_lo(x[kM + q].y), tf32_lo(x[kM + q].z), tf32_lo(x[kM + q].w));
+    for (int q = 0; q < 8; ++q)
+      dst[(q0 + q) * 32] = make_float4(tf32_lo(x[q].x), tf32_lo(x[q].y), tf32_lo(x[q].z), tf32_lo(x[q].w));
+  }
+}
+template <class Cfg>
+__device__ __forceinline__ void split_stage(uint8_t* stage, int lane) {
+  static_assert(Cfg::kMBytes % 4096 == 0 && Cfg::kNTileBytes % 4096 == 0, "tiles must be multiples of 4 KB");
+  split_region<Cfg>(stage, stage + Cfg::kOffMlo, Cfg::kMBytes, lane);
+  split_region<Cfg>(stage + Cfg::kOffN, stage + Cfg::kOffNlo, Cfg::kNTileBytes, lane);
 }
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi>
-__global__ void __launch_bounds__((TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL>::kThreads), 1)
+template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
+__global__ void __launch_bounds__((TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL, kCG>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
                const __grid_constant__ CUtensorMap tmH, const GemmParams p) {
   constexpr bool kStageH = (kEpi == TEPI_MU_KL);
-  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kStageH>;
+  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kStageH, kCG>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
-  constexpr uint32_t kIdesc = make_idesc(kFmtTF32, 128, kBlockT);
+  constexpr uint32_t kIdesc = make_idesc(kFmtTF32, 128 * kCG, kBlockT);
+  // does the MMA warp wait on the "ready" barrier (split and/or pair) or directly on the TMA barrier?
+  constexpr bool kUseReady = kSplit3 || kCG == 2;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[kStages];   // TMA bytes landed
-  __shared__ __align__(8) uint64_t bar_split[kStages];  // lo tiles written (3xTF32 only)
-  __shared__ __align__(8) uint64_t bar_empty[kStages];  // MMAs that read the stage retired
+  __shared__ __align__(8) uint64_t bar_full[kStages];   // this CTA's TMA bytes landed
+  __shared__ __align__(8) uint64_t bar_ready[kStages];  // (leader's copy is used) stage usable by the MMA: lo tiles
+                                                        // written / both CTAs of the pair loaded
+  __shared__ __align__(8) uint64_t bar_empty[kStages];  // MMAs that read the stage retired (both CTAs' copies fire)
   __shared__ __align__(8) uint64_t bar_acc_full[kAccStages];
-  __shared__ __align__(8) uint64_t bar_acc_empty[kAccStages];
+  __shared__ __align__(8) uint64_t bar_acc_empty[kAccStages];  // (leader's copy is used)
   __shared__ __align__(8) uint64_t bar_hfull[kHBufs];   // H chunk landed in shared memory
   __shared__ __align__(8) uint64_t bar_hready[kHBufs];  // the 4 epilogue warps of a chunk wrote the updated values
   __shared__ __align__(8) uint64_t bar_hempty[kHBufs];  // the TMA store has read the buffer
@@ -195,6 +214,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   uint8_t* ring_ptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t ring = smem_u32(ring_ptr);
 
@@ -204,12 +224,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (kStageH) tma_prefetch_desc(&tmH);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), 1);
-      mbar_init(smem_u32(&bar_split[i]), Cfg::kXformThreads / 32);  // one elected lane per split warp
+      mbar_init(smem_u32(&bar_ready[i]), Cfg::kReadyArrivals * kCG);
       mbar_init(smem_u32(&bar_empty[i]), 1);
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps);  // one elected lane of each epilogue warp
+      mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps * kCG);  // one elected lane of each epilogue warp
     }
     for (int i = 0; i < kHBufs; ++i) {
       mbar_init(smem_u32(&bar_hfull[i]), 1);
@@ -219,27 +239,71 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_base_smem), 512);
-    tmem_relinquish();
+    if (kCG == 2) { tmem_alloc2(smem_u32(&tmem_base_smem), 512); tmem_relinquish2(); }
+    else { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();  // peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   const int num_items = p.items_main + p.splits_last * p.num_t_tiles;
+  const int first_item = blockIdx.x / kCG, item_stride = gridDim.x / kCG;  // both CTAs of a pair walk the same items
+
+  // "stage ready" arrive: local barrier for a single CTA, the leader's copy for a pair
+  auto ready_arrive = [&](int stage) {
+    if (kCG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&bar_ready[stage]), 0));
+    else mbar_arrive(smem_u32(&bar_ready[stage]));
+  };
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      long long c_empty = 0;
+      const long long c_start = clock64();
+      // L2 look-ahead: the tiles of K-block (current + kAhead) are prefetched into L2 when the current one is
+      // loaded, so the ring refill sees L2 latency instead of HBM latency (the ring itself is only 3-6 deep).
+      constexpr int kAhead = 2 * kStages;
+      int la_item = first_item, la_kb = 0, la_kb1 = 0, la_m0 = 0, la_t0 = 0, la_count = 0, issued = 0;
+      bool la_valid = la_item < num_items;
+      if (la_valid) {
+        const WorkItem w = decode_item(p, la_item);
+        la_kb = w.kb0; la_kb1 = w.kb1;
+        la_m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
+        la_t0 = w.t_tile * kBlockT + (int)rank * Cfg::kNRows;
+      }
+      const bool use_la = !(p.debug_flags & (4 | 16));
+      for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
-        const int m0 = w.m_group * (128 * kMTiles);
-        const int t0 = w.t_tile * kBlockT;
+        const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
+        const int t0 = w.t_tile * kBlockT + (int)rank * Cfg::kNRows;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          while (use_la && la_valid && la_count < issued + kAhead) {
+            if (la_count >= issued + kStages) {  // (the first kStages blocks are about to be loaded anyway)
+              const int kc = la_kb * kBlockK;
+#pragma unroll
+              for (int i = 0; i < kMTiles; ++i)
+                if (la_m0 + i * Cfg::kRowsPerSub < p.M_total) tma_prefetch_l2_2d(&tmM, kc, la_m0 + i * Cfg::kRowsPerSub);
+              if (la_t0 < p.T) tma_prefetch_l2_2d(&tmN, kc, la_t0);
+            }
+            ++la_count;
+            if (++la_kb >= la_kb1) {
+              la_item += item_stride;
+              la_valid = la_item < num_items;
+              if (la_valid) {
+                const WorkItem w2 = decode_item(p, la_item);
+                la_kb = w2.kb0; la_kb1 = w2.kb1;
+                la_m0 = w2.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
+                la_t0 = w2.t_tile * kBlockT + (int)rank * Cfg::kNRows;
+              }
+            }
+          }
+          ++issued;
+          const long long c0 = clock64();
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          c_empty += clock64() - c0;
           const uint32_t full = smem_u32(&bar_full[stage]);
           if (p.debug_flags & 4) {
             mbar_arrive(full);
@@ -252,26 +316,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           // (sub-tiles past M_total are still loaded: TMA zero-fills them and the byte count stays constant)
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i)
-            tma_load_2d(sbase + i * Cfg::kMTileBytes, &tmM, kc, m0 + i * 128, full, kEvictNormal);
+            tma_load_2d(sbase + i * Cfg::kMTileBytes, &tmM, kc, m0 + i * Cfg::kRowsPerSub, full, kEvictNormal);
           tma_load_2d(sbase + Cfg::kOffN, &tmN, kc, t0, full, kEvictNormal);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (p.dbg_cycles) {
+        long long* o = p.dbg_cycles + (size_t)blockIdx.x * 8;
+        o[3] = clock64() - c_start; o[4] = c_empty;
+      }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (leader CTA of a pair only) =================
+    if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      long long c_acc = 0, c_ready = 0;
+      const long long c_start = clock64();
+      for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
-        const int m0 = w.m_group * (128 * kMTiles);
+        const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles);
         const int kb0 = w.kb0, kb1 = w.kb1;
-        mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        long long c0 = clock64();
+        if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        else mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        c_acc += clock64() - c0;
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
-          // 3xTF32: the split barrier fires after the TMA barrier and after the lo tiles are visible
-          mbar_wait(smem_u32(kSplit3 ? &bar_split[stage] : &bar_full[stage]), phase);
+          // 3xTF32 / pairs: the ready barrier fires after the TMA barrier(s) and after the lo tiles are visible
+          c0 = clock64();
+          if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_ready[stage]), phase);
+          else mbar_wait(smem_u32(kUseReady ? &bar_ready[stage] : &bar_full[stage]), phase);
+          c_ready += clock64() - c0;
           tc_fence_after();
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
           const uint32_t nbase = sbase + Cfg::kOffN;
@@ -279,7 +355,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const int ksteps = (kvalid + 7) >> 3;
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i) {
-            if (m0 + i * 128 >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
+            if (m0 + i * Cfg::kRowsPerSub >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
             if (p.debug_flags & 2) break;
             const uint32_t d = tmem_base + (uint32_t)((acc * kMTiles + i) * kBlockT);
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -290,28 +366,41 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                 const uint64_t a_lo =
                     make_smem_desc(sbase + Cfg::kOffMlo + i * Cfg::kMTileBytes + ks * 32, Cfg::kRowBytes);
                 const uint64_t b_lo = make_smem_desc(nbase + Cfg::kNTileBytes + ks * 32, Cfg::kRowBytes);
-                mma_tf32(d, a_lo, b_hi, kIdesc, accum);
-                mma_tf32(d, a_hi, b_lo, kIdesc, 1u);
-                mma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                if (kCG == 2) {
+                  mma_tf32_2cta(d, a_lo, b_hi, kIdesc, accum);
+                  mma_tf32_2cta(d, a_hi, b_lo, kIdesc, 1u);
+                  mma_tf32_2cta(d, a_hi, b_hi, kIdesc, 1u);
+                } else {
+                  mma_tf32(d, a_lo, b_hi, kIdesc, accum);
+                  mma_tf32(d, a_hi, b_lo, kIdesc, 1u);
+                  mma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                }
               } else {
-                mma_tf32(d, a_hi, b_hi, kIdesc, accum);
+                if (kCG == 2) mma_tf32_2cta(d, a_hi, b_hi, kIdesc, accum);
+                else mma_tf32(d, a_hi, b_hi, kIdesc, accum);
               }
             }
           }
-          mma_commit(smem_u32(&bar_empty[stage]));  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (kCG == 2) mma_commit_2cta(smem_u32(&bar_empty[stage])); else mma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(smem_u32(&bar_acc_full[acc]));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue(s)
+        if (kCG == 2) mma_commit_2cta(smem_u32(&bar_acc_full[acc])); else mma_commit(smem_u32(&bar_acc_full[acc]));
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (p.dbg_cycles) {
+        long long* o = p.dbg_cycles + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - c_start; o[1] = c_acc; o[2] = c_ready;
       }
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp) {
     // ================= H chunk loader: prefetches the activations the epilogue will update =================
     if (lane == 0) {
       int hbase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
-        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * 128;
+        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
         const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
         for (int c = 0; c < nch; ++c) {
           const int seq = hbase + c, b = seq % kHBufs;
@@ -328,9 +417,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     // ================= H chunk storer =================
     if (lane == 0) {
       int hbase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
-        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * 128;
+        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
         const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
         for (int c = 0; c < nch; ++c) {
           const int seq = hbase + c, b = seq % kHBufs;
@@ -345,20 +434,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       }
       tma_store_wait_all();
     }
-  } else if (warp >= Cfg::kFirstXformWarp) {
-    // ================= dedicated hi/lo split warps (3xTF32 with an overlapped epilogue) =================
-    if (Cfg::kDedicatedXform) {
-      const int tid = threadIdx.x - Cfg::kFirstXformWarp * 32;
+  } else if (Cfg::kRelay && warp == Cfg::kRelayWarp) {
+    // ================= pair without split warps: tell the leader when this CTA's stage has landed =================
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
-          if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, tid);
-          fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_split[stage]));
+          ready_arrive(stage);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= Cfg::kFirstXformWarp) {
+    // ================= dedicated hi/lo split warps (3xTF32 with an overlapped epilogue) =================
+    if (Cfg::kDedicatedXform) {
+      const int me = warp - Cfg::kFirstXformWarp;  // this warp owns K-blocks me, me + kSplitWarps, ...
+      int stage = 0, seq = 0;
+      uint32_t phase = 0;
+      for (int item = first_item; item < num_items; item += item_stride) {
+        const WorkItem w = decode_item(p, item);
+        for (int kb = w.kb0; kb < w.kb1; ++kb, ++seq) {
+          // every warp observes every phase of the barrier (a waiter that skipped phases could be fooled by
+          // parity aliasing two ring passes later); only the owner of the K-block does the work
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          if (seq % Cfg::kSplitWarps == me) {
+            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane);
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
+            __syncwarp();
+            if (lane == 0) ready_arrive(stage);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -366,33 +473,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   } else {
     // ================= epilogue: 8 warps.  Warp w may touch TMEM lanes [32*(w%4), +32); the two warps
     // of a lane quarter take alternate 32-column chunks, so each scheduler has two warps to overlap
-    // the global-memory round trips of the fused update. =================
+    // the memory round trips of the fused update. =================
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    int acc = 0, stage = 0, hbase = 0;
+    int acc = 0, stage = 0, hbase = 0, split_seq = 0;
     uint32_t acc_phase = 0, phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    long long c_accfull = 0, c_hfull = 0;
+    const long long c_estart = clock64();
+    for (int item = first_item; item < num_items; item += item_stride) {
       const WorkItem w = decode_item(p, item);
       const int m_group = w.m_group, split = w.split;
       const int t0 = w.t_tile * kBlockT;
       if (kSplit3 && !Cfg::kDedicatedXform) {
         // single accumulator stage: these warps have nothing to drain during the main loop, so they
-        // produce the lo tiles
-        const int tid = threadIdx.x - 64;
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, tid);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_split[stage]));
+        // produce the lo tiles, one warp per K-block round-robin
+        const int me = warp - 2;
+        for (int kb = w.kb0; kb < w.kb1; ++kb, ++split_seq) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);  // (all warps see all phases; see the dedicated warps)
+          if (split_seq % Cfg::kSplitWarps == me) {
+            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ready_arrive(stage);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      long long c0 = clock64();
       mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+      c_accfull += clock64() - c0;
       tc_fence_after();
       if (kStageH) {
         // ---- fused multiplicative update through the shared-memory H chunks ----
-        const int m = m_group * 128 + quarter * 32 + lane;
+        const int m = m_group * Cfg::kRowsPerSub + (int)rank * 128 + quarter * 32 + lane;
         float den = ((m < p.M_total) ? p.colsum[m] : 1.f) + p.lam;
         if (den == 0.f) den = p.eps;
         const float inv_den = __frcp_rn(den);
@@ -402,7 +515,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockT + c * 32), v);
+          c0 = clock64();
           mbar_wait(smem_u32(&bar_hfull[b]), ph);
+          c_hfull += clock64() - c0;
           float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * kHBufBytes) + quarter * 32 + lane;
           float h[32];
 #pragma unroll
@@ -431,37 +546,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) sv[j] = h[j] * a;
             const float tot = warp_transpose_sum(sv, lane);
-            p.left_out[((size_t)(m_group * 4 + quarter) * p.n_left + l) * p.left_ld + (t0 + c * 32 + lane)] = tot;
+            const int prow = (m_group * kCG + (int)rank) * 4 + quarter;  // one partial row per 32 exemplars
+            p.left_out[((size_t)prow * p.n_left + l) * p.left_ld + (t0 + c * 32 + lane)] = tot;
           }
         }
         hbase += nch;
       }
 #pragma unroll
       for (int i = 0; i < (kStageH ? 0 : kMTiles); ++i) {
-        const int mrow0 = m_group * (128 * kMTiles) + i * 128;
-        if (mrow0 >= p.M_total) break;  // whole sub-tile is padding (warp-uniform)
+        const int mrow0 = m_group * (Cfg::kRowsPerSub * kMTiles) + i * Cfg::kRowsPerSub + (int)rank * 128;
+        if (m_group * (Cfg::kRowsPerSub * kMTiles) + i * Cfg::kRowsPerSub >= p.M_total) break;  // whole MMA is padding
         const int m = mrow0 + quarter * 32 + lane;
         const bool m_ok = m < p.M_total;
-        float inv_den = 1.f;
-        if (kEpi == TEPI_MU_KL) {
-          float den = (m_ok ? p.colsum[m] : 1.f) + p.lam;
-          if (den == 0.f) den = p.eps;
-          inv_den = __frcp_rn(den);
-        }
-        // chunks of this warp: c = half, half+2, ...  The H values of the NEXT chunk are requested before the
-        // current one is processed (fast path), so a warp always has a full chunk of loads in flight.
         const bool rows_full = (mrow0 + 128 <= p.M_total) && (p.row_active == nullptr);
-        float hn[32];
-        bool hn_valid = false;
-        if (kEpi != TEPI_PARTIAL) {
-          const int tb0 = t0 + half * 32;
-          if (rows_full && tb0 + 32 <= p.T) {
-            const float* o0 = p.out + (size_t)tb0 * p.ld_out + m;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) hn[j] = o0[(size_t)j * p.ld_out];
-            hn_valid = true;
-          }
-        }
         for (int c = half; c < kBlockT / 32; c += 2) {
           const int tb = t0 + c * 32;
           if (tb >= p.T) break;  // warp-uniform
@@ -470,10 +567,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const uint32_t taddr =
               tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * kMTiles + i) * kBlockT + c * 32);
           tmem_ld_32x32(taddr, v);
+          tmem_ld_wait();
           // whole chunk in range, every lane a real row, no frozen utterances: straight-line code
           const bool fast = (tb + 32 <= p.T) && rows_full;
           if (kEpi == TEPI_PARTIAL) {
-            tmem_ld_wait();
             float* o = p.out + ((size_t)split * p.T + tb) * p.ld_out + m;
             if (fast) {
 #pragma unroll
@@ -483,52 +580,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
               for (int j = 0; j < 32; ++j)
                 if (m_ok && tb + j < p.T) o[(size_t)j * p.ld_out] = __uint_as_float(v[j]);
             }
-          } else {
+          } else {  // TEPI_MU_FRO (register path)
             float* o = p.out + (size_t)tb * p.ld_out + m;
-            const float* q = (kEpi == TEPI_MU_FRO) ? p.num0 + (size_t)tb * p.ld_out + m : nullptr;
-            if (fast && hn_valid) {
-              float h[32];
+            const float* q = p.num0 + (size_t)tb * p.ld_out + m;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) h[j] = hn[j];
-              // prefetch the next chunk of this warp
-              const int tbn = tb + 64;
-              hn_valid = (c + 2 < kBlockT / 32) && (tbn + 32 <= p.T);
-              if (hn_valid) {
-                const float* on = p.out + (size_t)tbn * p.ld_out + m;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) hn[j] = on[(size_t)j * p.ld_out];
-              }
-              tmem_ld_wait();
-              if (kEpi == TEPI_MU_FRO) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  float dn = __uint_as_float(v[j]) + p.lam;
-                  if (dn == 0.f) dn = p.eps;
-                  h[j] = h[j] * __fdividef(q[(size_t)j * p.ld_out], dn);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[(size_t)j * p.ld_out] = h[j];
-            } else {
-              hn_valid = false;
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const bool ok = m_ok && (tb + j < p.T) && (!p.row_active || p.row_active[tb + j]);
-                if (ok) {
-                  float hv = o[(size_t)j * p.ld_out];
-                  if (kEpi == TEPI_MU_FRO) {
-                    float dn = __uint_as_float(v[j]) + p.lam;
-                    if (dn == 0.f) dn = p.eps;
-                    hv = hv * __fdividef(q[(size_t)j * p.ld_out], dn);
-                  } else {
-                    hv = hv * (__uint_as_float(v[j]) * inv_den);
-                  }
-                  o[(size_t)j * p.ld_out] = hv;
-                }
+            for (int j = 0; j < 32; ++j) {
+              const bool ok = m_ok && (tb + j < p.T) && (!p.row_active || p.row_active[tb + j]);
+              if (ok) {
+                float dn = __uint_as_float(v[j]) + p.lam;
+                if (dn == 0.f) dn = p.eps;
+                o[(size_t)j * p.ld_out] = o[(size_t)j * p.ld_out] * __fdividef(q[(size_t)j * p.ld_out], dn);
               }
             }
           }
@@ -536,17 +597,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+      if (lane == 0) {
+        if (kCG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&bar_acc_empty[acc]), 0));
+        else mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (p.dbg_cycles && warp == 2 && lane == 0) {
+      long long* o = p.dbg_cycles + (size_t)blockIdx.x * 8;
+      o[5] = clock64() - c_estart; o[6] = c_accfull; o[7] = c_hfull;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  // nobody leaves (and frees shared memory / TMEM the leader's MMAs may still read) before both CTAs are done
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kCG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -711,11 +780,11 @@ inline int check_alignment(int mode, const float* H, int ldH) {
   return EVC_OK;
 }
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi>
+template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
 inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const GemmParams& p,
                      cudaStream_t s) {
-  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL>;
-  auto kern = tc_gemm_kernel<kMTiles, kBlockT, kBlockK, kSplit3, kEpi>;
+  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL, kCG>;
+  auto kern = tc_gemm_kernel<kMTiles, kBlockT, kBlockK, kSplit3, kEpi, kCG>;
   static bool configured = false;
   if (!configured) {
     EVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -723,12 +792,45 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
   }
   const int items = p.items_main + p.splits_last * p.num_t_tiles;
   if (items <= 0) return EVC_OK;
-  const int grid = items < num_sms() ? items : num_sms();
+  const int slots = num_sms() / kCG;  // CTAs (kCG = 1) or CTA pairs (kCG = 2) resident at once
+  const int grid = (items < slots ? items : slots) * kCG;
   static const int dbg = getenv("EVC_DEBUG_FLAGS") ? atoi(getenv("EVC_DEBUG_FLAGS")) : 0;
   GemmParams q = p;
   q.debug_flags = dbg;
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(tmM, tmN, tmH, q);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static const bool timing = getenv("EVC_DEBUG_TIMING") != nullptr;
+  static long long* dbuf = nullptr;
+  static int prints = 0;
+  if (timing) {
+    if (!dbuf) EVC_CUDA(cudaMalloc(&dbuf, 8 * sizeof(long long) * 1024));
+    EVC_CUDA(cudaMemsetAsync(dbuf, 0, 8 * sizeof(long long) * grid, s));
+    q.dbg_cycles = dbuf;
+  }
+  EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, q));
   EVC_LAUNCH_CHECK();
+  if (timing && prints < 6) {
+    std::vector<long long> h((size_t)grid * 8);
+    EVC_CUDA(cudaStreamSynchronize(s));
+    EVC_CUDA(cudaMemcpy(h.data(), dbuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double a[8] = {0}; int nl = 0;
+    for (int b = 0; b < grid; b += kCG) { for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)b * 8 + k]; ++nl; }
+    fprintf(stderr, "[evc timing] kernel<%d,%d,%d,%d,%d,cg%d> grid %d (leaders avg, cycles): mma loop %.0f (wait acc_empty %.0f, wait ready %.0f) | "
+            "producer loop %.0f (wait empty %.0f) | epilogue warp loop %.0f (wait acc_full %.0f, wait hfull %.0f)\n",
+            kMTiles, kBlockT, kBlockK, (int)kSplit3, kEpi, kCG, grid, a[0] / nl, a[1] / nl, a[2] / nl, a[3] / nl, a[4] / nl,
+            a[5] / nl, a[6] / nl, a[7] / nl);
+    ++prints;
+  }
   return EVC_OK;
 }
 
@@ -737,6 +839,12 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
 constexpr int kC1MTiles = 2, kC1BlockT = 256;  // contraction 1 / conversion: 256 dictionary rows x 256 frames, split-K
 constexpr int kC2MTiles = 1, kC2BlockT = 256;  // contraction 2: 128 exemplars x 256 frames, 2 accumulator stages
 constexpr int kBlockK3 = 16, kBlockK1 = 32;
+
+// CTA group of the MMAs: 2 (CTA pairs, default) or 1 (EVC_CTA_GROUP=1: single-CTA kernels, kept for A/B runs).
+inline int cta_group() {
+  static const int cg = (getenv("EVC_CTA_GROUP") && atoi(getenv("EVC_CTA_GROUP")) == 1) ? 1 : 2;
+  return cg;
+}
 
 // Resident tensor-core operands of one dictionary.  All fp32: the hi operand of 3xTF32 is the raw value
 // (the MMA truncates it), the lo operand is derived in shared memory, so HBM holds one copy per layout.
@@ -793,7 +901,9 @@ struct C1Plan {
 };
 inline C1Plan plan_c1(int F, int N, int T, int bk) {
   C1Plan pl{};
-  const int tiles = ceil_div(F, 128);
+  const int cg = cta_group();
+  const int sub_rows = 128 * cg;  // dictionary rows of one MMA
+  const int tiles = ceil_div(F, sub_rows);
   pl.m_groups = ceil_div(tiles, kC1MTiles);
   pl.t_tiles = ceil_div(T, kC1BlockT);
   pl.kb_total = ceil_div(N, bk);
@@ -801,17 +911,18 @@ inline C1Plan plan_c1(int F, int N, int T, int bk) {
   const int tiles_last = tiles - (pl.m_groups - 1) * kC1MTiles;
   const bool partial = tiles_last < kC1MTiles;
   const int full_groups = partial ? pl.m_groups - 1 : pl.m_groups;
-  pl.f_last = partial ? full_groups * kC1MTiles * 128 : F;
+  pl.f_last = partial ? full_groups * kC1MTiles * sub_rows : F;
   // w = sub-tile K-blocks per CTA; grow it until the items fit the SMs
+  const int slots = num_sms() / cg;  // CTAs or CTA pairs resident at once
   long long total = (long long)tiles * pl.kb_total * pl.t_tiles;
-  int w = (int)std::max<long long>(1, (total + num_sms() - 1) / num_sms());
+  int w = (int)std::max<long long>(1, (total + slots - 1) / slots);
   for (;; ++w) {
     const int per = std::max(1, ceil_div(w, kC1MTiles));
     const int sf = full_groups ? ceil_div(pl.kb_total, std::min(per, pl.kb_total)) : 0;
     const int per_l = std::max(1, ceil_div(w, tiles_last));
     const int sl = partial ? ceil_div(pl.kb_total, std::min(per_l, pl.kb_total)) : 0;
     const long long items = (long long)pl.t_tiles * (full_groups * sf + sl);
-    if (items <= num_sms() || (sf <= 1 && sl <= 1)) {
+    if (items <= slots || (sf <= 1 && sl <= 1)) {
       pl.splits = sf; pl.kb_per_split = std::min(per, pl.kb_total);
       pl.splits_last = sl; pl.kb_per_split_last = std::min(per_l, pl.kb_total);
       break;
@@ -824,7 +935,7 @@ inline C1Plan plan_c1(int F, int N, int T, int bk) {
 // Called before a solve / product: make sure the workspace can hold the split-K partials.
 // Workspace layout: [ split-K partials | leftover-row partials of the fused update ].
 inline size_t ws_left_offset(const C1Plan& pl, int T) { return round_up_sz((size_t)pl.max_splits * T * pl.ldp, 64); }
-inline int left_rows(const DictOperands& o) { return ceil_div(o.N, 128) * 4; }
+inline int left_rows(const DictOperands& o) { return round_up(ceil_div(o.N, 128), 2) * 4; }
 inline int left_ld(int T) { return round_up(T, kC2BlockT); }
 
 inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, int T, DevBuf* ws, cudaStream_t s) {
@@ -849,7 +960,7 @@ inline int launch_ratio(const float* X, int ldX, const float* WH, int ldWH, floa
   return EVC_OK;
 }
 
-template <bool kSplit3>
+template <bool kSplit3, int kCG>
 inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
                          DevBuf* ws, cudaStream_t s, const RatioArgs* ra) {
   constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;
@@ -857,7 +968,7 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   float* partials = ws->as<float>();
   float* leftp = ws->as<float>() + ws_left_offset(pl, T);
   CUtensorMap tmH;
-  EVC_TRY(make_tmap(&tmH, H, T, o.N, ldH, bk, kC1BlockT));
+  EVC_TRY(make_tmap(&tmH, H, T, o.N, ldH, bk, kC1BlockT / kCG));
   GemmParams p{};
   p.M_total = o.F_main; p.T = T; p.K = o.N;
   p.num_m_groups = pl.m_groups; p.num_t_tiles = pl.t_tiles; p.num_splits = pl.splits;
@@ -867,7 +978,7 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   p.out = partials; p.ld_out = pl.ldp;
   {
     ProfScope ps(0, s);
-    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL>(target ? o.tmBT : o.tmAT, tmH, tmH, p, s)));
+    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL, kCG>(target ? o.tmBT : o.tmAT, tmH, tmH, p, s)));
   }
   // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
   const bool from_partials = o.n_left > 0 && !target && o.left_valid;
@@ -901,18 +1012,22 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
 inline int contract_wh(DictOperands& o, int mode, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
                        DevBuf* ws, cudaStream_t s, const RatioArgs* ra = nullptr) {
   if (target && !o.has_target) return fail(EVC_ERR_INVALID_ARGUMENT, "no target dictionary");
-  if (mode == EVC_MODE_3XTF32) return contract_wh_t<true>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
-  return contract_wh_t<false>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  if (cta_group() == 2) {
+    if (mode == EVC_MODE_3XTF32) return contract_wh_t<true, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+    return contract_wh_t<false, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  }
+  if (mode == EVC_MODE_3XTF32) return contract_wh_t<true, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  return contract_wh_t<false, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
 }
 
 // Second contraction with a fused epilogue.  `R` is what multiplies A^T: the ratio (KL) or A H (Frobenius).
-template <bool kSplit3, int kEpi>
-inline int contract2_t(DictOperands& o, int T, const float* R, int ldR, GemmParams p, cudaStream_t s) {
+template <bool kSplit3, int kEpi, int kCG>
+inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmParams p, cudaStream_t s) {
   constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;
   CUtensorMap tmR;
-  EVC_TRY(make_tmap(&tmR, R, T, o.F, ldR, bk, kC2BlockT));
+  EVC_TRY(make_tmap(&tmR, R, T, o.F, ldR, bk, kC2BlockT / kCG));
   p.M_total = o.N; p.T = T; p.K = o.F;
-  p.num_m_groups = ceil_div(o.N, 128 * kC2MTiles); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
+  p.num_m_groups = ceil_div(o.N, 128 * kC2MTiles * kCG); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(o.F, bk); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
   // neighbouring CTAs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
@@ -920,7 +1035,13 @@ inline int contract2_t(DictOperands& o, int T, const float* R, int ldR, GemmPara
   CUtensorMap tmHc = tmR;  // only the fused KL update stages H through shared memory
   if (kEpi == TEPI_MU_KL) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
   ProfScope ps(2, s);
-  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi>(o.tmA, tmR, tmHc, p, s);
+  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi, kCG>(o.tmA, tmR, tmHc, p, s);
+}
+
+template <bool kSplit3, int kEpi>
+inline int contract2_t(DictOperands& o, int T, const float* R, int ldR, const GemmParams& p, cudaStream_t s) {
+  if (cta_group() == 2) return contract2_cg<kSplit3, kEpi, 2>(o, T, R, ldR, p, s);
+  return contract2_cg<kSplit3, kEpi, 1>(o, T, R, ldR, p, s);
 }
 
 inline int update_kl(DictOperands& o, int mode, const float* X, int ldX, int T, const float* WH, int ldWH, float* R,
