@@ -51,10 +51,10 @@ struct GemmParams {
   // the fused update accumulates their share of the NEXT A*H, sum_n h_new[t,n] * A[n, F_main+l], per warp.
   const float* left_a;  // (n_left, left_lda): rows F_main.. of the transposed dictionary (contiguous in n)
   int left_lda, n_left;
-  float* left_out;      // [(m_group*4 + quarter)][l][t] partial sums, pitch left_ld
-  int left_ld;
+  float* left_out;      // [l][t][row] partial sums, row = 4*(128-exemplar block) + lane quarter
+  int left_ld, left_rows;  // frames pitch, rows pitch
   long long* dbg_cycles;  // EVC_DEBUG_TIMING: per-CTA [8] cycle counters of the role threads (nullptr = off)
-  int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops, 16 no L2 look-ahead prefetch
+  int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops, 16 enable the L2 look-ahead prefetch
 };
 
 // vals[j] (j = 0..31) per lane -> returns, in lane L, the sum over all 32 lanes of vals[L]  (31 shuffles).
@@ -108,7 +108,8 @@ __device__ __forceinline__ float tf32_lo(float x) {
 }
 
 constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, interleaved over 32-column chunks
-constexpr int kXformWarps = 4;  // dedicated hi/lo split warps (only when the epilogue overlaps the main loop)
+constexpr int kXformWarps = 8;  // dedicated hi/lo split warps (only when the epilogue overlaps the main loop)
+constexpr int kWarpsPerStage = 2;  // split warps that share one ring stage (groups take K-blocks round-robin)
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 // The fused-update epilogue stages H through shared memory in [32 frames x 128 exemplars] chunks moved by TMA
@@ -145,8 +146,9 @@ struct TileCfg {
   // A pair without split warps still needs someone to tell the leader that the peer's TMA bytes landed.
   static constexpr bool kRelay = (kCG == 2) && !kSplit3;
   // arrivals per CTA on the leader's "stage ready" barrier
-  static constexpr int kReadyArrivals = 1;  // the warp that owns the stage (split warps take K-blocks round-robin)
   static constexpr int kSplitWarps = kXformThreads > 0 ? kXformThreads / 32 : 1;
+  static constexpr int kSplitGroups = kSplit3 ? kSplitWarps / kWarpsPerStage : 1;  // groups take K-blocks round-robin
+  static constexpr int kReadyArrivals = kSplit3 ? kWarpsPerStage : 1;  // the warps of the group that owns the stage
   static constexpr int kFirstXformWarp = 2 + kEpiWarps;
   static constexpr int kRelayWarp = kFirstXformWarp + (kDedicatedXform ? kXformWarps : 0);
   static constexpr int kLoaderWarp = kRelayWarp + (kRelay ? 1 : 0);  // H chunk loader, then storer
@@ -168,24 +170,27 @@ struct TileCfg {
 // so several stages are split concurrently instead of all warps sharing one.  16 B per lane per access,
 // batches of 8 loads in flight.
 template <class Cfg>
-__device__ __forceinline__ void split_region(const uint8_t* hi, uint8_t* lo, int bytes, int lane) {
-  const float4* src = reinterpret_cast<const float4*>(hi) + lane;
-  float4* dst = reinterpret_cast<float4*>(lo) + lane;
-  const int n = bytes / 16 / 32;  // float4 per lane (a multiple of 8: tiles are >= 4 KB)
-  for (int q0 = 0; q0 < n; q0 += 8) {
-    float4 x[8];
+__device__ __forceinline__ void split_region(const uint8_t* hi, uint8_t* lo, int bytes, int lane, int part) {
+  // this warp's share: a contiguous 1/kWarpsPerStage of the region
+  const int share = bytes / kWarpsPerStage;
+  const float4* src = reinterpret_cast<const float4*>(hi + part * share) + lane;
+  float4* dst = reinterpret_cast<float4*>(lo + part * share) + lane;
+  const int n = share / 16 / 32;  // float4 per lane (a multiple of 4: tiles are >= 4 KB)
+  for (int q0 = 0; q0 < n; q0 += 4) {
+    float4 x[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) x[q] = src[(q0 + q) * 32];
+    for (int q = 0; q < 4; ++q) x[q] = src[(q0 + q) * 32];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < 4; ++q)
       dst[(q0 + q) * 32] = make_float4(tf32_lo(x[q].x), tf32_lo(x[q].y), tf32_lo(x[q].z), tf32_lo(x[q].w));
   }
 }
 template <class Cfg>
-__device__ __forceinline__ void split_stage(uint8_t* stage, int lane) {
-  static_assert(Cfg::kMBytes % 4096 == 0 && Cfg::kNTileBytes % 4096 == 0, "tiles must be multiples of 4 KB");
-  split_region<Cfg>(stage, stage + Cfg::kOffMlo, Cfg::kMBytes, lane);
-  split_region<Cfg>(stage + Cfg::kOffN, stage + Cfg::kOffNlo, Cfg::kNTileBytes, lane);
+__device__ __forceinline__ void split_stage(uint8_t* stage, int lane, int part) {
+  static_assert(Cfg::kMBytes % (4096 * kWarpsPerStage) == 0 && Cfg::kNTileBytes % (4096 * kWarpsPerStage) == 0,
+                "every split warp must get a multiple of 2 KB per region");
+  split_region<Cfg>(stage, stage + Cfg::kOffMlo, Cfg::kMBytes, lane, part);
+  split_region<Cfg>(stage + Cfg::kOffN, stage + Cfg::kOffNlo, Cfg::kNTileBytes, lane, part);
 }
 
 template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
@@ -211,6 +216,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_hready[kHBufs];  // the 4 epilogue warps of a chunk wrote the updated values
   __shared__ __align__(8) uint64_t bar_hempty[kHBufs];  // the TMA store has read the buffer
   __shared__ uint32_t tmem_base_smem;
+  __shared__ long long dbg_t_issue[kStages];  // EVC_DEBUG_TIMING: clock at TMA issue per stage
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -274,7 +280,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         la_m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
         la_t0 = w.t_tile * kBlockT + (int)rank * Cfg::kNRows;
       }
-      const bool use_la = !(p.debug_flags & (4 | 16));
+      // measured: no gain (the ring refill is not HBM-latency bound) and the extra issue slots slow the
+      // single producer thread down, so the look-ahead is off unless debug flag 16 asks for it
+      const bool use_la = (p.debug_flags & 16) && !(p.debug_flags & 4);
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
@@ -311,6 +319,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             continue;
           }
           mbar_arrive_expect_tx(full, (uint32_t)Cfg::kLoadBytes);
+          if (p.dbg_cycles) dbg_t_issue[stage] = clock64();
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
           const int kc = kb * kBlockK;
           // (sub-tiles past M_total are still loaded: TMA zero-fills them and the byte count stays constant)
@@ -454,20 +463,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       const int me = warp - Cfg::kFirstXformWarp;  // this warp owns K-blocks me, me + kSplitWarps, ...
       int stage = 0, seq = 0;
       uint32_t phase = 0;
+      long long d_tma = 0, d_split = 0, d_n = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++seq) {
           // every warp observes every phase of the barrier (a waiter that skipped phases could be fooled by
           // parity aliasing two ring passes later); only the owner of the K-block does the work
           mbar_wait(smem_u32(&bar_full[stage]), phase);
-          if (seq % Cfg::kSplitWarps == me) {
-            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane);
+          if (seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
+            const long long t1 = clock64();
+            if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
+            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
             fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
             __syncwarp();
             if (lane == 0) ready_arrive(stage);
+            if (p.dbg_cycles && lane == 0) d_split += clock64() - t1;
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+      }
+      if (p.dbg_cycles && lane == 0) {
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(p.dbg_cycles + (size_t)(gridDim.x + blockIdx.x) * 8);
+        atomicAdd(o + 0, (unsigned long long)d_tma); atomicAdd(o + 1, (unsigned long long)d_split);
+        atomicAdd(o + 2, (unsigned long long)d_n);
       }
     }
   } else {
@@ -478,7 +496,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     const int half = (warp - 2) >> 2;
     int acc = 0, stage = 0, hbase = 0, split_seq = 0;
     uint32_t acc_phase = 0, phase = 0;
-    long long c_accfull = 0, c_hfull = 0;
+    long long c_accfull = 0, c_hfull = 0, d_tma = 0, d_split = 0, d_n = 0;
     const long long c_estart = clock64();
     for (int item = first_item; item < num_items; item += item_stride) {
       const WorkItem w = decode_item(p, item);
@@ -490,11 +508,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int me = warp - 2;
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++split_seq) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);  // (all warps see all phases; see the dedicated warps)
-          if (split_seq % Cfg::kSplitWarps == me) {
-            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane);
+          if (split_seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
+            const long long t1 = clock64();
+            if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
+            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ready_arrive(stage);
+            if (p.dbg_cycles && lane == 0) d_split += clock64() - t1;
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -547,7 +568,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) sv[j] = h[j] * a;
             const float tot = warp_transpose_sum(sv, lane);
             const int prow = (m_group * kCG + (int)rank) * 4 + quarter;  // one partial row per 32 exemplars
-            p.left_out[((size_t)prow * p.n_left + l) * p.left_ld + (t0 + c * 32 + lane)] = tot;
+            p.left_out[((size_t)l * p.left_ld + (t0 + c * 32 + lane)) * p.left_rows + prow] = tot;
           }
         }
         hbase += nch;
@@ -607,6 +628,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       long long* o = p.dbg_cycles + (size_t)blockIdx.x * 8;
       o[5] = clock64() - c_estart; o[6] = c_accfull; o[7] = c_hfull;
     }
+    if (p.dbg_cycles && lane == 0 && kSplit3 && !Cfg::kDedicatedXform) {
+      unsigned long long* o = reinterpret_cast<unsigned long long*>(p.dbg_cycles + (size_t)(gridDim.x + blockIdx.x) * 8);
+      atomicAdd(o + 0, (unsigned long long)d_tma); atomicAdd(o + 1, (unsigned long long)d_split);
+      atomicAdd(o + 2, (unsigned long long)d_n);
+    }
   }
 
   tc_fence_before();
@@ -622,15 +648,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 // ---- memory-bound helpers ------------------------------------------------------------------------
 
 // WH[t,f] = sum_s P[s][t][f] for the tensor-core rows f < F_main (fixed order: deterministic);
-// WH[t,F_main+l] = sum_r L[r][l][t] from the fused update's per-warp partials when `left_rows` > 0.
+// WH[t,F_main+l] = sum_r L[l][t][r] from the fused update's per-warp partials when `left_rows` > 0 (the block
+// that owns those columns reduces the `left_rows` contiguous partials of its frame first).
 // With `R` != nullptr it also emits the ratio R = X / max(WH, eps) (zero pad columns) in the same pass.
-__global__ void reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp,
-                                       int F, int F_main, float* __restrict__ WH, int ldwh,
-                                       const float* __restrict__ L, int left_rows, int n_left, int left_ld,
-                                       const float* __restrict__ X, int ldx, float* __restrict__ R, int ldr, float eps) {
+__global__ void __launch_bounds__(128)
+reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
+                       float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
+                       int left_ld, const float* __restrict__ X, int ldx, float* __restrict__ R, int ldr, float eps) {
+  __shared__ float s_left[8];
+  __shared__ float s_warp[4];
   const int f = blockIdx.y * blockDim.x + threadIdx.x;
   const int t = blockIdx.x;
   if (t >= T) return;
+  const bool owns_left = left_rows > 0 && (int)blockIdx.y == F_main / (int)blockDim.x;
+  if (owns_left) {
+    for (int l = 0; l < n_left; ++l) {
+      const float* row = L + ((size_t)l * left_ld + t) * left_rows;
+      float a = 0.f;
+      for (int r = threadIdx.x; r < left_rows; r += blockDim.x) a += row[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = a;
+      __syncthreads();
+      if (threadIdx.x == 0) s_left[l] = (s_warp[0] + s_warp[1]) + (s_warp[2] + s_warp[3]);
+      __syncthreads();
+    }
+  }
   float s = 0.f;
   bool have = false;
   if (f < F_main) {
@@ -638,32 +681,11 @@ __global__ void reduce_partials_kernel(const float* __restrict__ P, int S, int S
     for (int k = 0; k < n; ++k) s += P[((size_t)k * T + t) * ldp + f];
     have = true;
   } else if (f < F && left_rows > 0) {
-    const int l = f - F_main;
-    for (int r = 0; r < left_rows; ++r) s += L[((size_t)r * n_left + l) * left_ld + t];
+    s = s_left[f - F_main];
     have = true;
   }
   if (f < ldwh && (have || f >= F)) WH[(size_t)t * ldwh + f] = s;
   if (R && f < ldr) R[(size_t)t * ldr + f] = (have && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s, eps)) : 0.f;
-}
-
-// Collapse the fused update's per-warp leftover partials L[r][l][t] (r = m_group*4 + quarter) to one row per
-// leftover column: out[l][t] = sum_r L[r][l][t].  Block = 32 frames x 32 row groups, fixed order (deterministic).
-__global__ void __launch_bounds__(1024)
-left_reduce_kernel(const float* __restrict__ L, int rows, int n_left, int ld, int T, float* __restrict__ out) {
-  __shared__ float red[32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int t = blockIdx.x * 32 + tx, l = blockIdx.y;
-  float acc = 0.f;
-  if (t < T)
-    for (int r = ty; r < rows; r += 32) acc += L[((size_t)r * n_left + l) * ld + t];
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && t < T) {
-    float v = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v += red[k][tx];
-    out[(size_t)l * ld + t] = v;
-  }
 }
 
 // Standalone leftover rows: WH[t, F_main+l] = sum_n H[t,n] * a[l][n].  One block per frame; used whenever the
@@ -814,13 +836,13 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
   static int prints = 0;
   if (timing) {
     if (!dbuf) EVC_CUDA(cudaMalloc(&dbuf, 8 * sizeof(long long) * 1024));
-    EVC_CUDA(cudaMemsetAsync(dbuf, 0, 8 * sizeof(long long) * grid, s));
+    EVC_CUDA(cudaMemsetAsync(dbuf, 0, 8 * sizeof(long long) * grid * 2, s));
     q.dbg_cycles = dbuf;
   }
   EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, q));
   EVC_LAUNCH_CHECK();
   if (timing && prints < 6) {
-    std::vector<long long> h((size_t)grid * 8);
+    std::vector<long long> h((size_t)grid * 16);
     EVC_CUDA(cudaStreamSynchronize(s));
     EVC_CUDA(cudaMemcpy(h.data(), dbuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     double a[8] = {0}; int nl = 0;
@@ -829,6 +851,9 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
             "producer loop %.0f (wait empty %.0f) | epilogue warp loop %.0f (wait acc_full %.0f, wait hfull %.0f)\n",
             kMTiles, kBlockT, kBlockK, (int)kSplit3, kEpi, kCG, grid, a[0] / nl, a[1] / nl, a[2] / nl, a[3] / nl, a[4] / nl,
             a[5] / nl, a[6] / nl, a[7] / nl);
+    double tma = 0, spl = 0, cnt = 0;
+    for (int b = 0; b < grid; ++b) { tma += (double)h[(size_t)(grid + b) * 8]; spl += (double)h[(size_t)(grid + b) * 8 + 1]; cnt += (double)h[(size_t)(grid + b) * 8 + 2]; }
+    if (cnt > 0) fprintf(stderr, "[evc timing]    per K-block: TMA issue -> landed %.0f cycles, landed -> split done + ready arrive %.0f cycles (%.0f blocks)\n", tma / cnt, spl / cnt, cnt);
     ++prints;
   }
   return EVC_OK;
@@ -935,7 +960,7 @@ inline C1Plan plan_c1(int F, int N, int T, int bk) {
 // Called before a solve / product: make sure the workspace can hold the split-K partials.
 // Workspace layout: [ split-K partials | leftover-row partials of the fused update ].
 inline size_t ws_left_offset(const C1Plan& pl, int T) { return round_up_sz((size_t)pl.max_splits * T * pl.ldp, 64); }
-inline int left_rows(const DictOperands& o) { return round_up(ceil_div(o.N, 128), 2) * 4; }
+inline int left_rows(const DictOperands& o) { return round_up(ceil_div(o.N, 128), cta_group()) * 4; }
 inline int left_ld(int T) { return round_up(T, kC2BlockT); }
 
 inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, int T, DevBuf* ws, cudaStream_t s) {
@@ -943,7 +968,7 @@ inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, i
   const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
   const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
   o.left_valid = false;
-  const size_t left = (size_t)(left_rows(o) + 1) * o.n_left * left_ld(T);  // per-warp partials + their sum
+  const size_t left = (size_t)left_rows(o) * o.n_left * left_ld(T);
   return ws->reserve((ws_left_offset(pl, T) + left) * sizeof(float));
 }
 
@@ -985,17 +1010,11 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   const bool standalone = o.n_left > 0 && !from_partials;
   {
     ProfScope ps(1, s);
-    float* leftsum = leftp + (size_t)left_rows(o) * o.n_left * left_ld(T);
-    if (from_partials) {
-      dim3 lg(ceil_div(T, 32), o.n_left), lb(32, 32);
-      left_reduce_kernel<<<lg, lb, 0, s>>>(leftp, left_rows(o), o.n_left, left_ld(T), T, leftsum);
-      EVC_LAUNCH_CHECK();
-    }
     const int cols = std::max(ldWH, ra ? ra->ldR : 0);
     dim3 g(T, ceil_div(cols, 128));
     const bool fuse = ra && !standalone;
     reduce_partials_kernel<<<g, 128, 0, s>>>(partials, pl.splits, pl.splits_last, pl.f_last, T, pl.ldp, o.F, o.F_main, WH,
-                                             ldWH, leftsum, from_partials ? 1 : 0, o.n_left, left_ld(T),
+                                             ldWH, leftp, from_partials ? left_rows(o) : 0, o.n_left, left_ld(T),
                                              fuse ? ra->X : nullptr, fuse ? ra->ldX : 0, fuse ? ra->R : nullptr,
                                              fuse ? ra->ldR : 0, fuse ? ra->eps : 0.f);
     EVC_LAUNCH_CHECK();
@@ -1055,7 +1074,7 @@ inline int update_kl(DictOperands& o, int mode, const float* X, int ldX, int T, 
     const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
     const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
     p.left_a = o.AT + (size_t)o.F_main * o.ldN; p.left_lda = o.ldN; p.n_left = o.n_left;
-    p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T);
+    p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T); p.left_rows = left_rows(o);
     o.left_valid = true;  // (stream order: the partials are complete before the next contraction 1 reads them)
   }
   if (mode == EVC_MODE_3XTF32) return contract2_t<true, TEPI_MU_KL>(o, T, R, ldR, p, s);
