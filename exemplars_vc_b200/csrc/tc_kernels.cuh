@@ -40,6 +40,7 @@ struct GemmParams {
   // fewer, longer K splits so every CTA carries the same number of MMAs.  items_main = work items of the
   // other groups; 0 splits_last means "no special last group".
   int items_main, splits_last, kblocks_per_split_last;
+  int direct_store;  // fused update: write H straight from registers (1) instead of shared memory + TMA store (0)
   int m_fastest;  // work-item order: 1 = consecutive CTAs take consecutive dictionary-row groups of one frame tile
   float* out;    // PARTIAL: [split][t][m] with pitch ld_out;  MU_*: the activations H (T, ld_out)
   int ld_out;
@@ -240,7 +241,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     for (int i = 0; i < kHBufs; ++i) {
       mbar_init(smem_u32(&bar_hfull[i]), 1);
       mbar_init(smem_u32(&bar_hready[i]), 4);
-      mbar_init(smem_u32(&bar_hempty[i]), 1);
+      mbar_init(smem_u32(&bar_hempty[i]), p.direct_store ? 4 : 1);
     }
     fence_barrier_init();
   }
@@ -424,7 +425,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp + 1) {
     // ================= H chunk storer =================
-    if (lane == 0) {
+    if (lane == 0 && !p.direct_store) {
       int hbase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item);
@@ -553,13 +554,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (tb + j < p.T && p.row_active[tb + j]) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
           }
-          if (!(p.debug_flags & 8)) {
+          if (p.direct_store) {
+            // registers -> global, 128 B per warp per frame; the chunk buffer is free as soon as it was read
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_hempty[b]));
+            if (m < p.M_total && !(p.debug_flags & 8)) {
+              float* o = p.out + (size_t)(t0 + c * 32) * p.ld_out + m;
+              const int rows = min(32, p.T - (t0 + c * 32));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) hb[j * 128] = h[j];
+              for (int j = 0; j < 32; ++j)
+                if (j < rows) o[(size_t)j * p.ld_out] = h[j];
+            }
+          } else {
+            if (!(p.debug_flags & 8)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) hb[j * 128] = h[j];
+            }
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_hready[b]));
           }
-          fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA store
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_hready[b]));
           for (int l = 0; l < p.n_left; ++l) {
             // (rows past T and exemplars past N were zero-filled by TMA: they add nothing)
             const float a = (m < p.M_total) ? p.left_a[(size_t)l * p.left_lda + m] : 0.f;
@@ -1051,6 +1065,7 @@ inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmPar
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
   // neighbouring CTAs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
   p.m_fastest = getenv("EVC_T_FASTEST") ? 0 : 1;
+  p.direct_store = getenv("EVC_DIRECT_STORE") ? 1 : 0;
   CUtensorMap tmHc = tmR;  // only the fused KL update stages H through shared memory
   if (kEpi == TEPI_MU_KL) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
   ProfScope ps(2, s);
