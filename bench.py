@@ -293,7 +293,8 @@ def main():
                     "mma_passes_per_product": passes,
                     "us_per_launch": per_launch_s * 1e6,
                     "step_share": {k: round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4) for k, v in prof.items()},
-                    "contraction1_us_per_launch": c1_ms / max(c1_n, 1) * 1e3}
+                    "contraction1_us_per_launch": c1_ms / max(c1_n, 1) * 1e3,
+                    "class_ms_launches": {k: [round(v[0], 3), v[1]] for k, v in prof.items()}}
         total_flop = (4.0 * wl.iterations + 2.0) * wl.T * wl.F * wl.N * (1 if exemplar_sharded else world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,

@@ -81,6 +81,7 @@ int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH
     EVC_TRY(tc::contract_wh(d->tc_ops, d->mode, H, ldH, T, WH, ldWH, target, &d->tcws, s, ra));
   }
   if (d->comm && d->comm->world > 1) {
+    ProfScope ps(3, s);  // exemplar sharding: the per-iteration exchange of the partial A*H
     EVC_TRY(nccl::all_reduce_sum(d->comm->comm, WH, (size_t)T * ldWH, s));
   }
   return EVC_OK;

@@ -111,3 +111,16 @@ def test_synth_generator_matches_oracle_gen():
     assert np.array_equal(X, X2)
     X3 = synth.frames(123, A2, 6)
     assert X3.shape == X.shape and X3.min() > 0
+
+
+def test_real_speech_fixture_reduced_config1():
+    """BASELINE.json configs[0] in reduced form (oracle/make_golden_speech.py): spectra of the reference's own
+    wav files, 768 DTW-aligned exemplar pairs, 64 frames of utterance 100162."""
+    g = load_golden("speech_sf1_tf1_100162")
+    X, A, B = (g[k].astype(np.float64) for k in ("X", "A", "B"))
+    W, n_iter, obj = o.kl_mu(X, A, tol=float(g["tol"]), max_iter=int(g["max_iter"]))
+    assert n_iter == int(g["n_iter"])
+    assert rel_fro(W, g["W"]) < 1e-6            # golden W is stored in float32
+    assert abs(obj - float(g["objective"])) / float(g["objective"]) < 1e-9
+    assert rel_fro(o.convert(W, B), g["Y"]) < 1e-6
+    assert (W < 1e-6 * W.max()).mean() > 0.5     # activations of real speech over exemplars are sparse

@@ -239,3 +239,16 @@ def test_host_buffer_c_abi_entry_point():
                                                          Y.ctypes.data, 201, C.byref(p), C.byref(res), None))
     assert res.n_iter == int(g["n_iter"])
     assert rel_fro(H, g["W"]) < 1e-3 and rel_fro(Y, g["Y"]) < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "3xtf32", "tf32"])
+def test_real_speech_reduced_config1(mode):
+    """BASELINE.json configs[0] in reduced form: real spectra (60 dB dynamic range, sparse activations)."""
+    g = load_golden("speech_sf1_tf1_100162")
+    act, H, Y = _solve(mode, g["X"], g["A"], g["B"], tol=float(g["tol"]), max_iter=int(g["max_iter"]))
+    tol_h, tol_obj = TOL[mode]
+    if mode in ACCURATE:
+        assert act.n_iter == int(g["n_iter"])
+    assert rel_fro(H, g["W"]) < tol_h, rel_fro(H, g["W"])
+    assert rel_fro(Y, g["Y"]) < tol_h, rel_fro(Y, g["Y"])
+    assert abs(act.objective - float(g["objective"])) / float(g["objective"]) < tol_obj
