@@ -253,6 +253,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   if (kCG == 2) cluster_sync_all(); else __syncthreads();  // peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous
+  // kernel in the stream; from here on its results are needed
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_items = p.items_main + p.splits_last * p.num_t_tiles;
   const int first_item = blockIdx.x / kCG, item_stride = gridDim.x / kCG;  // both CTAs of a pair walk the same items
@@ -669,13 +673,14 @@ __global__ void __launch_bounds__(128)
 reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
                        float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
                        int left_ld, const float* __restrict__ X, int ldx, float* __restrict__ R, int ldr, float eps) {
+  // one block per frame; a thread owns groups of 4 consecutive columns (16-byte loads of the partials)
   __shared__ float s_left[8];
   __shared__ float s_warp[4];
-  const int f = blockIdx.y * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
   const int t = blockIdx.x;
   if (t >= T) return;
-  const bool owns_left = left_rows > 0 && (int)blockIdx.y == F_main / (int)blockDim.x;
-  if (owns_left) {
+  if (left_rows > 0) {
     for (int l = 0; l < n_left; ++l) {
       const float* row = L + ((size_t)l * left_ld + t) * left_rows;
       float a = 0.f;
@@ -688,18 +693,40 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
       __syncthreads();
     }
   }
-  float s = 0.f;
-  bool have = false;
-  if (f < F_main) {
-    const int n = (f >= f_last) ? S_last : S;  // columns of the last row group have their own split count
-    for (int k = 0; k < n; ++k) s += P[((size_t)k * T + t) * ldp + f];
-    have = true;
-  } else if (f < F && left_rows > 0) {
-    s = s_left[f - F_main];
-    have = true;
+  const int cols = max(ldwh, R ? ldr : 0);
+  for (int f0 = threadIdx.x * 4; f0 < cols; f0 += blockDim.x * 4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    bool have[4] = {false, false, false, false};
+    if (f0 + 4 <= F_main && (f0 >= f_last || f0 + 4 <= f_last)) {
+      const int n = (f0 >= f_last) ? S_last : S;  // columns of the last row group have their own split count
+      const float* p0 = P + (size_t)t * ldp + f0;
+      for (int k = 0; k < n; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(p0 + (size_t)k * T * ldp);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      }
+      have[0] = have[1] = have[2] = have[3] = true;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = f0 + j;
+        if (f < F_main) {
+          const int n = (f >= f_last) ? S_last : S;
+          for (int k = 0; k < n; ++k) s[j] += P[((size_t)k * T + t) * ldp + f];
+          have[j] = true;
+        } else if (f < F && left_rows > 0) {
+          s[j] = s_left[f - F_main];
+          have[j] = true;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = f0 + j;
+      if (f < ldwh && (have[j] || f >= F)) WH[(size_t)t * ldwh + f] = s[j];
+      if (R && f < ldr)
+        R[(size_t)t * ldr + f] = (have[j] && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s[j], eps)) : 0.f;
+    }
   }
-  if (f < ldwh && (have || f >= F)) WH[(size_t)t * ldwh + f] = s;
-  if (R && f < ldr) R[(size_t)t * ldr + f] = (have && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s, eps)) : 0.f;
 }
 
 // Standalone leftover rows: WH[t, F_main+l] = sum_n H[t,n] * a[l][n].  One block per frame; used whenever the
@@ -816,6 +843,12 @@ inline int check_alignment(int mode, const float* H, int ldH) {
   return EVC_OK;
 }
 
+// Programmatic dependent launch between the kernels of an iteration (EVC_NO_PDL=1 turns it off).
+inline bool use_pdl() {
+  static const bool on = getenv("EVC_NO_PDL") == nullptr;
+  return on;
+}
+
 template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
 inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const GemmParams& p,
                      cudaStream_t s) {
@@ -838,13 +871,15 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
   static const bool timing = getenv("EVC_DEBUG_TIMING") != nullptr;
   static long long* dbuf = nullptr;
   static int prints = 0;
@@ -1024,13 +1059,18 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   const bool standalone = o.n_left > 0 && !from_partials;
   {
     ProfScope ps(1, s);
-    const int cols = std::max(ldWH, ra ? ra->ldR : 0);
-    dim3 g(T, ceil_div(cols, 128));
+    dim3 g(T, 1);
     const bool fuse = ra && !standalone;
-    reduce_partials_kernel<<<g, 128, 0, s>>>(partials, pl.splits, pl.splits_last, pl.f_last, T, pl.ldp, o.F, o.F_main, WH,
-                                             ldWH, leftp, from_partials ? left_rows(o) : 0, o.n_left, left_ld(T),
-                                             fuse ? ra->X : nullptr, fuse ? ra->ldX : 0, fuse ? ra->R : nullptr,
-                                             fuse ? ra->ldR : 0, fuse ? ra->eps : 0.f);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = g; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
+    EVC_CUDA(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, (const float*)partials, pl.splits, pl.splits_last, pl.f_last, T,
+                                pl.ldp, o.F, o.F_main, WH, ldWH, (const float*)leftp, from_partials ? left_rows(o) : 0,
+                                o.n_left, left_ld(T), fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0,
+                                fuse ? ra->R : (float*)nullptr, fuse ? ra->ldR : 0, fuse ? ra->eps : 0.f));
     EVC_LAUNCH_CHECK();
     if (standalone) {
       const float* rows = (target ? o.BT : o.AT) + (size_t)o.F_main * o.ldN;
