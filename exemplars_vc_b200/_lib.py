@@ -63,6 +63,7 @@ def lib():
     L.evc_objective.argtypes = [vp, vp, ip, ip, vp, ip, ip, fp, C.POINTER(C.c_double), vp]
     L.evc_factorize_convert_host.argtypes = [vp, vp, ip, ip, vp, ip, vp, ip, C.POINTER(SolveParams),
                                              C.POINTER(SolveResult), vp]
+    L.evc_gather_stack.argtypes = [vp, ip, ip, ip, vp, vp, vp, ip, ip, vp, ip, vp]
     L.evc_profile_enable.argtypes = [vp, ip]
     L.evc_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(ip)]
     L.evc_comm_unique_id.argtypes = [C.c_char_p]
@@ -71,7 +72,7 @@ def lib():
     L.evc_dict_attach_comm.argtypes = [vp, vp, ip]
     for name in ("evc_dict_create", "evc_dict_destroy", "evc_dict_info", "evc_dict_colsum", "evc_solve",
                  "evc_solve_batched", "evc_convert", "evc_reconstruct", "evc_objective", "evc_factorize_convert_host",
-                 "evc_profile_enable", "evc_profile_read", "evc_comm_unique_id", "evc_comm_create", "evc_comm_destroy", "evc_dict_attach_comm"):
+                 "evc_gather_stack", "evc_profile_enable", "evc_profile_read", "evc_comm_unique_id", "evc_comm_create", "evc_comm_destroy", "evc_dict_attach_comm"):
         getattr(L, name).restype = ip
     _lib = L
     return L

@@ -488,6 +488,19 @@ int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total) {
   return EVC_OK;
 }
 
+int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int* idx, const int* lo, const int* hi,
+                     int n_out, int context, float* out, int ld_out, void* stream) {
+  if (!frames || !idx || !lo || !hi || !out || F < 1 || n_frames < 1 || n_out < 0 || context < 0 || ld < F ||
+      ld_out < (2 * context + 1) * F)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_gather_stack: bad argument");
+  if (n_out == 0) return EVC_OK;
+  const int width = (2 * context + 1) * F;
+  dim3 g(n_out, ceil_div(width, 1024) < 1 ? 1 : ceil_div(width, 1024));
+  simt::gather_stack_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(frames, ld, F, idx, lo, hi, n_out, context, out, ld_out);
+  EVC_LAUNCH_CHECK();
+  return EVC_OK;
+}
+
 int evc_profile_enable(evc_dict_t d, int on) {
   if (!d) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_profile_enable: null handle");
   d->prof.on = on != 0;

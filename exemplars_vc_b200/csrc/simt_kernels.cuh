@@ -239,5 +239,21 @@ __global__ void transpose_kernel(const float* __restrict__ src, int ld_src, floa
   }
 }
 
+// out[k, (d+c)*F + f] = frames[clamp(idx[k]+d, lo[k], hi[k]-1), f]: aligned-frame gather + context stacking.
+__global__ void gather_stack_kernel(const float* __restrict__ frames, int ld, int F, const int* __restrict__ idx,
+                                    const int* __restrict__ lo, const int* __restrict__ hi, int n_out, int context,
+                                    float* __restrict__ out, int ld_out) {
+  const int k = blockIdx.x;
+  if (k >= n_out) return;
+  const int width = (2 * context + 1) * F;
+  const int base = idx[k], l = lo[k], h = hi[k] - 1;
+  for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < width; c += gridDim.y * blockDim.x) {
+    const int d = c / F - context, f = c - (c / F) * F;
+    int r = base + d;
+    r = r < l ? l : (r > h ? h : r);
+    out[(size_t)k * ld_out + c] = frames[(size_t)r * ld + f];
+  }
+}
+
 }  // namespace simt
 }  // namespace evc

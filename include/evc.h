@@ -156,6 +156,18 @@ int evc_comm_create(const char id[128], int rank, int world, evc_comm_t* out);
 int evc_comm_destroy(evc_comm_t c);
 int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total);
 
+/*
+ * Dictionary construction on the device: aligned-frame gather with optional +-context frame
+ * stacking.  Replaces the Python double loop that gathers frames by DTW index (04_align_n_nmf.py:113-124) and
+ * the list.extend / np.asarray stacking (04_align_n_nmf.py:230-246); context > 0 builds the stacked exemplars of
+ * BASELINE.json's F = 2565 configuration ((2*context+1) * F features per row).
+ *   out[k, (d+context)*F + f] = frames[clamp(idx[k] + d, lo[k], hi[k]-1), f]      d = -context..context
+ * frames (n_frames, F) pitch ld; idx / lo / hi: n_out device ints (frame index and the [lo, hi) range of the file
+ * the frame belongs to, so stacking never crosses a file boundary); out (n_out, (2*context+1)*F) pitch ld_out.
+ */
+int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int* idx, const int* lo, const int* hi,
+                     int n_out, int context, float* out, int ld_out, void* stream);
+
 /* Diagnostics: number of kernels this library has launched in this process. */
 long long evc_kernel_launch_count(void);
 

@@ -1,5 +1,5 @@
 """Run the BASELINE.json configs that are not the bench line at (near) full size on one GPU: a few iterations,
-timing per iteration, and a float64 spot check of a handful of frames.  Usage: python tools/config_check.py"""
+timing per iteration, and a float64 spot check of a handful of frames.  Usage: python tests/manual/config_check.py"""
 import os
 import sys
 import time
@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from exemplars_vc_b200 import ExemplarDictionary, synth  # noqa: E402
 from oracle import nmf_oracle as o  # noqa: E402
 

@@ -1,5 +1,5 @@
 """GPU diagnostics (not a test): per-mode errors of both contractions and of a short solve, printed even
-when something is badly off, so one gpurun call tells what to fix.  Usage: python tools/gpu_diag.py"""
+when something is badly off, so one gpurun call tells what to fix.  Usage: python tests/manual/gpu_diag.py"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import traceback
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from exemplars_vc_b200 import ExemplarDictionary, synth  # noqa: E402
 from oracle import nmf_oracle as o  # noqa: E402
 

@@ -252,3 +252,37 @@ def test_real_speech_reduced_config1(mode):
     assert rel_fro(H, g["W"]) < tol_h, rel_fro(H, g["W"])
     assert rel_fro(Y, g["Y"]) < tol_h, rel_fro(Y, g["Y"])
     assert abs(act.objective - float(g["objective"])) / float(g["objective"]) < tol_obj
+
+
+def test_device_dictionary_gather_and_context_stacking():
+    """aligned-frame gather (04_align_n_nmf.py:113-124, 230-246) + +-2 frame stacking on the device."""
+    from exemplars_vc_b200 import features
+    rng = np.random.default_rng(12)
+    F = 37
+    src = [rng.random((n, F)).astype(np.float32) for n in (11, 5, 23)]
+    tar = [rng.random((n, F)).astype(np.float32) for n in (9, 8, 20)]
+    sp = [np.sort(rng.integers(0, len(s), size=14)) for s in src]
+    tp = [np.sort(rng.integers(0, len(t), size=14)) for t in tar]
+
+    def ref(files, paths, c):
+        rows = []
+        for m, p in zip(files, paths):
+            for k in p:
+                rows.append(np.concatenate([m[min(max(k + d, 0), len(m) - 1)] for d in range(-c, c + 1)]))
+        return np.asarray(rows)
+
+    for c in (0, 2):
+        d = features.build_dictionaries(src, tar, sp, tp, context=c, mode="fp32")
+        assert (d.N, d.F) == (42, (2 * c + 1) * F)
+        A_ref, B_ref = ref(src, sp, c), ref(tar, tp, c)
+        H = np.eye(42, dtype=np.float32)
+        assert np.array_equal(d.to_host(d.reconstruct(H)), A_ref)      # identity activations read the dictionary back
+        assert np.array_equal(d.to_host(d.convert(H)), B_ref)
+        d.close()
+    X = rng.random((6, F)).astype(np.float32)
+    Xs = features.stack_frames(X, 2).cpu().numpy()
+    assert np.array_equal(Xs, ref([X], [np.arange(6)], 2))
+    # reference-style per-file dicts with a key, |real(stft)| taken as in 04_align_n_nmf.py:323
+    d = features.build_dictionaries([{"real": -s} for s in src], [{"real": t} for t in tar], sp, tp, key="real", mode="fp32")
+    assert np.array_equal(d.to_host(d.reconstruct(np.eye(42, dtype=np.float32))), ref(src, sp, 0))
+    d.close()
