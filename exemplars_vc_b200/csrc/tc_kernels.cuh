@@ -41,6 +41,9 @@ struct GemmParams {
   // other groups; 0 splits_last means "no special last group".
   int items_main, splits_last, kblocks_per_split_last;
   int direct_store;  // fused update: write H straight from registers (1) instead of shared memory + TMA store (0)
+  // Tail balancing of contraction 2: tiles with index >= half_from are processed as two half-width items (t_cols =
+  // kBlockT/2 frames each) so the last, partly filled round costs half a tile time.  half_from = items_main: off.
+  int half_from;
   int m_fastest;  // work-item order: 1 = consecutive CTAs take consecutive dictionary-row groups of one frame tile
   float* out;    // PARTIAL: [split][t][m] with pitch ld_out;  MU_*: the activations H (T, ld_out)
   int ld_out;
@@ -75,9 +78,19 @@ __device__ __forceinline__ float warp_transpose_sum(float (&vals)[32], int lane)
 
 struct WorkItem {
   int m_group, t_tile, split, kb0, kb1;
+  int t_off, t_cols;  // frame offset inside the frame tile and number of frame columns of this item
 };
-__device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item) {
+__device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item, int block_t) {
   WorkItem w;
+  w.t_off = 0;
+  w.t_cols = block_t;
+  if (item >= p.half_from && p.half_from < p.items_main) {
+    // half-width tail items of contraction 2 (no split-K there): tile = half_from + h/2, half = h & 1
+    const int h = item - p.half_from;
+    item = p.half_from + (h >> 1);
+    w.t_cols = block_t / 2;
+    w.t_off = (h & 1) * w.t_cols;
+  }
   if (item < p.items_main) {
     const int groups = p.splits_last ? p.num_m_groups - 1 : p.num_m_groups;
     if (p.m_fastest) {
@@ -258,7 +271,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   pdl_wait();
   pdl_launch_dependents();
 
-  const int num_items = p.items_main + p.splits_last * p.num_t_tiles;
+  const int num_items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
   const int first_item = blockIdx.x / kCG, item_stride = gridDim.x / kCG;  // both CTAs of a pair walk the same items
 
   // "stage ready" arrive: local barrier for a single CTA, the leader's copy for a pair
@@ -280,18 +293,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       int la_item = first_item, la_kb = 0, la_kb1 = 0, la_m0 = 0, la_t0 = 0, la_count = 0, issued = 0;
       bool la_valid = la_item < num_items;
       if (la_valid) {
-        const WorkItem w = decode_item(p, la_item);
+        const WorkItem w = decode_item(p, la_item, kBlockT);
         la_kb = w.kb0; la_kb1 = w.kb1;
         la_m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
-        la_t0 = w.t_tile * kBlockT + (int)rank * Cfg::kNRows;
+        la_t0 = w.t_tile * kBlockT + w.t_off + (int)rank * (w.t_cols / kCG);
       }
       // measured: no gain (the ring refill is not HBM-latency bound) and the extra issue slots slow the
       // single producer thread down, so the look-ahead is off unless debug flag 16 asks for it
       const bool use_la = (p.debug_flags & 16) && !(p.debug_flags & 4);
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item);
+        const WorkItem w = decode_item(p, item, kBlockT);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
-        const int t0 = w.t_tile * kBlockT + (int)rank * Cfg::kNRows;
+        // (a half-width item still loads a kNRows-row box: the narrower MMA never reads the surplus rows)
+        const int t0 = w.t_tile * kBlockT + w.t_off + (int)rank * (w.t_cols / kCG);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           while (use_la && la_valid && la_count < issued + kAhead) {
             if (la_count >= issued + kStages) {  // (the first kStages blocks are about to be loaded anyway)
@@ -306,10 +320,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
               la_item += item_stride;
               la_valid = la_item < num_items;
               if (la_valid) {
-                const WorkItem w2 = decode_item(p, la_item);
+                const WorkItem w2 = decode_item(p, la_item, kBlockT);
                 la_kb = w2.kb0; la_kb1 = w2.kb1;
                 la_m0 = w2.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
-                la_t0 = w2.t_tile * kBlockT + (int)rank * Cfg::kNRows;
+                la_t0 = w2.t_tile * kBlockT + w2.t_off + (int)rank * (w2.t_cols / kCG);
               }
             }
           }
@@ -348,9 +362,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       long long c_acc = 0, c_ready = 0;
       const long long c_start = clock64();
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item);
+        const WorkItem w = decode_item(p, item, kBlockT);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles);
         const int kb0 = w.kb0, kb1 = w.kb1;
+        const uint32_t idesc = (w.t_cols == kBlockT) ? kIdesc : make_idesc(kFmtTF32, 128 * kCG, (uint32_t)w.t_cols);
         long long c0 = clock64();
         if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
         else mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
@@ -381,17 +396,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                     make_smem_desc(sbase + Cfg::kOffMlo + i * Cfg::kMTileBytes + ks * 32, Cfg::kRowBytes);
                 const uint64_t b_lo = make_smem_desc(nbase + Cfg::kNTileBytes + ks * 32, Cfg::kRowBytes);
                 if (kCG == 2) {
-                  mma_tf32_2cta(d, a_lo, b_hi, kIdesc, accum);
-                  mma_tf32_2cta(d, a_hi, b_lo, kIdesc, 1u);
-                  mma_tf32_2cta(d, a_hi, b_hi, kIdesc, 1u);
+                  mma_tf32_2cta(d, a_lo, b_hi, idesc, accum);
+                  mma_tf32_2cta(d, a_hi, b_lo, idesc, 1u);
+                  mma_tf32_2cta(d, a_hi, b_hi, idesc, 1u);
                 } else {
-                  mma_tf32(d, a_lo, b_hi, kIdesc, accum);
-                  mma_tf32(d, a_hi, b_lo, kIdesc, 1u);
-                  mma_tf32(d, a_hi, b_hi, kIdesc, 1u);
+                  mma_tf32(d, a_lo, b_hi, idesc, accum);
+                  mma_tf32(d, a_hi, b_lo, idesc, 1u);
+                  mma_tf32(d, a_hi, b_hi, idesc, 1u);
                 }
               } else {
-                if (kCG == 2) mma_tf32_2cta(d, a_hi, b_hi, kIdesc, accum);
-                else mma_tf32(d, a_hi, b_hi, kIdesc, accum);
+                if (kCG == 2) mma_tf32_2cta(d, a_hi, b_hi, idesc, accum);
+                else mma_tf32(d, a_hi, b_hi, idesc, accum);
               }
             }
           }
@@ -413,9 +428,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (lane == 0) {
       int hbase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item);
-        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
-        const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
+        const WorkItem w = decode_item(p, item, kBlockT);
+        const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
+        const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = 0; c < nch; ++c) {
           const int seq = hbase + c, b = seq % kHBufs;
           const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
@@ -432,9 +447,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (lane == 0 && !p.direct_store) {
       int hbase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item);
-        const int t0 = w.t_tile * kBlockT, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
-        const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
+        const WorkItem w = decode_item(p, item, kBlockT);
+        const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
+        const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = 0; c < nch; ++c) {
           const int seq = hbase + c, b = seq % kHBufs;
           const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
@@ -454,7 +469,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item);
+        const WorkItem w = decode_item(p, item, kBlockT);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           ready_arrive(stage);
@@ -470,7 +485,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       uint32_t phase = 0;
       long long d_tma = 0, d_split = 0, d_n = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item);
+        const WorkItem w = decode_item(p, item, kBlockT);
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++seq) {
           // every warp observes every phase of the barrier (a waiter that skipped phases could be fooled by
           // parity aliasing two ring passes later); only the owner of the K-block does the work
@@ -504,9 +519,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     long long c_accfull = 0, c_hfull = 0, d_tma = 0, d_split = 0, d_n = 0;
     const long long c_estart = clock64();
     for (int item = first_item; item < num_items; item += item_stride) {
-      const WorkItem w = decode_item(p, item);
+      const WorkItem w = decode_item(p, item, kBlockT);
       const int m_group = w.m_group, split = w.split;
-      const int t0 = w.t_tile * kBlockT;
+      const int t0 = w.t_tile * kBlockT + w.t_off;
       if (kSplit3 && !Cfg::kDedicatedXform) {
         // single accumulator stage: these warps have nothing to drain during the main loop, so they
         // produce the lo tiles, one warp per K-block round-robin
@@ -535,7 +550,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         float den = ((m < p.M_total) ? p.colsum[m] : 1.f) + p.lam;
         if (den == 0.f) den = p.eps;
         const float inv_den = __frcp_rn(den);
-        const int nch = min(kBlockT / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT);
+        const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = half; c < nch; c += 2) {
           const int seq = hbase + c, b = seq % kHBufs;
           const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
@@ -598,7 +613,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int m = mrow0 + quarter * 32 + lane;
         const bool m_ok = m < p.M_total;
         const bool rows_full = (mrow0 + 128 <= p.M_total) && (p.row_active == nullptr);
-        for (int c = half; c < kBlockT / 32; c += 2) {
+        for (int c = half; c < w.t_cols / 32; c += 2) {
           const int tb = t0 + c * 32;
           if (tb >= p.T) break;  // warp-uniform
           if (p.debug_flags & 8) continue;
@@ -859,7 +874,7 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
     EVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int items = p.items_main + p.splits_last * p.num_t_tiles;
+  const int items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
   if (items <= 0) return EVC_OK;
   const int slots = num_sms() / kCG;  // CTAs (kCG = 1) or CTA pairs (kCG = 2) resident at once
   const int grid = (items < slots ? items : slots) * kCG;
@@ -1049,6 +1064,7 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   p.kblocks_per_split = pl.kb_per_split; p.kblocks_total = pl.kb_total;
   p.splits_last = pl.splits_last; p.kblocks_per_split_last = pl.kb_per_split_last;
   p.items_main = (pl.splits_last ? pl.m_groups - 1 : pl.m_groups) * pl.t_tiles * pl.splits;
+  p.half_from = p.items_main;
   p.out = partials; p.ld_out = pl.ldp;
   {
     ProfScope ps(0, s);
@@ -1103,6 +1119,12 @@ inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmPar
   p.num_m_groups = ceil_div(o.N, 128 * kC2MTiles * kCG); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(o.F, bk); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
+  {
+    // tail balancing: the tiles of a last, less-than-half-filled round run as two half-width items each
+    const int slots = num_sms() / kCG, rem = p.items_main % slots;
+    static const bool allow = getenv("EVC_NO_HALF_TILES") == nullptr;
+    p.half_from = (allow && p.items_main > slots && rem > 0 && 2 * rem <= slots) ? p.items_main - rem : p.items_main;
+  }
   // neighbouring CTAs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
   p.m_fastest = getenv("EVC_T_FASTEST") ? 0 : 1;
   p.direct_store = getenv("EVC_DIRECT_STORE") ? 1 : 0;
