@@ -234,8 +234,10 @@ def main():
     launches0 = _lib.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    enqueue_ms = 0.0
     for _ in range(args.steps):
         act, y = step_resident()
+        enqueue_ms += float(_lib.lib().evc_last_enqueue_ms())
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -305,7 +307,7 @@ def main():
                            "mode": args.mode, "sharding": ("exemplar" if exemplar_sharded else "utterance") if world > 1 else "none",
                            "l2": "working set (H 80 MB + dictionary operands > 160 MB) exceeds the 126 MB L2; no flush needed"},
                 "tflops_algorithmic": total_flop / (ms_step * 1e-3) / 1e12,
-                "objective": act.objective, "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+                "objective": act.objective, "host_enqueue_ms_per_step": enqueue_ms / args.steps, "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_step,
                         "h2d_bytes_per_step": int(x_pinned.numel() * 4),
                         "d2h_bytes_per_step": int(yh.size * 4 + hh.size * 4)}}

@@ -11,6 +11,7 @@
 #include "tc_kernels.cuh"
 #include "nccl_shim.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <new>
 
@@ -44,6 +45,8 @@ struct evc_dict {
 };
 
 namespace {
+
+thread_local double g_last_enqueue_ms = 0.0;
 
 int reserve_workspace(evc_dict* d, int T, int ldH, bool need_num0) {
   d->ldWH = round_up(d->F, 4);
@@ -223,6 +226,8 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
   const bool fuse_ratio = d->mode != EVC_MODE_FP32 && loss == EVC_LOSS_KL && !(d->comm && d->comm->world > 1);
   const tc::RatioArgs ra{X, ldX, d->R.as<float>(), d->ldR, eps};
   bool wh_fresh = true;  // WH = H A of the current H is in the workspace (the objective at init just made it)
+  const auto enq0 = std::chrono::steady_clock::now();
+  double sync_ms = 0.0;
   for (int k = 1; k <= p->max_iter && n_active > 0; ++k) {
     const float lam = p->lambda + (float)k * p->lambda_step;
     const unsigned char* mask = any_frozen ? d->active.as<unsigned char>() : nullptr;
@@ -236,7 +241,9 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
     else EVC_TRY(update_fro(d, T, H, ldH, num0, lam, eps, mask, s));
 
     if (p->tol > 0.f && k % p->check_every == 0) {  // sklearn :867-879
+      const auto c0 = std::chrono::steady_clock::now();
       EVC_TRY(objective_segments(d, X, ldX, T, H, ldH, loss, eps, seg, err, s));
+      sync_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
       wh_fresh = true;  // the next iteration reuses this A*H (sklearn recomputes it, _nmf.py:554 after :868)
       bool changed = false;
       for (int u = 0; u < nseg; ++u) {
@@ -254,6 +261,9 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
       }
     }
   }
+
+  g_last_enqueue_ms =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - enq0).count() - sync_ms;
 
   if (res) {
     EVC_TRY(objective_segments(d, X, ldX, T, H, ldH, loss, eps, seg, err, s));
@@ -277,6 +287,7 @@ extern "C" {
 int evc_version(void) { return EVC_VERSION; }
 const char* evc_last_error_string(void) { return g_err; }
 long long evc_kernel_launch_count(void) { return g_launches.load(); }
+double evc_last_enqueue_ms(void) { return g_last_enqueue_ms; }
 
 void evc_default_params(evc_solve_params* p) {
   if (!p) return;

@@ -168,6 +168,10 @@ int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total);
 int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int* idx, const int* lo, const int* hi,
                      int n_out, int context, float* out, int ld_out, void* stream);
 
+/* Diagnostics: host milliseconds the last evc_solve* on this thread spent ENQUEUEING its iteration loop (if this
+ * approaches the device time of the loop, the GPU is waiting for the host). */
+double evc_last_enqueue_ms(void);
+
 /* Diagnostics: number of kernels this library has launched in this process. */
 long long evc_kernel_launch_count(void);
 
