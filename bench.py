@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--iterations", type=int, default=None, help="override the workload's iteration count")
     ap.add_argument("--ref-sample-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="exemplar sharding: ncclAllReduce instead of the peer-memory kernel")
     args = ap.parse_args()
 
     from exemplars_vc_b200 import synth
@@ -197,7 +198,8 @@ def main():
         # every rank draws the same stream and keeps its rows, so the dictionary equals the 1-GPU one
         A_full, B_full = synth.dictionaries(seed, wl.F, wl.N)
         X_host = synth.frames(seed, A_full, wl.T)
-        d = sharding.make_exemplar_sharded(lambda a, b: A_full[a:b], lambda a, b: B_full[a:b], wl.N, mode=args.mode)
+        d = sharding.make_exemplar_sharded(lambda a, b: A_full[a:b], lambda a, b: B_full[a:b], wl.N, mode=args.mode,
+                                           p2p=not args.no_p2p, max_frames=wl.T)
         del A_full, B_full, rngA
     else:
         A, B = synth.dictionaries(seed, wl.F, wl.N)
@@ -305,6 +307,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": wl.name, "F": wl.F, "N": wl.N, "T": wl.T, "iterations": wl.iterations,
                            "mode": args.mode, "sharding": ("exemplar" if exemplar_sharded else "utterance") if world > 1 else "none",
+                           "all_reduce": getattr(d, "all_reduce", None),
                            "l2": "working set (H 80 MB + dictionary operands > 160 MB) exceeds the 126 MB L2; no flush needed"},
                 "tflops_algorithmic": total_flop / (ms_step * 1e-3) / 1e12,
                 "objective": act.objective, "host_enqueue_ms_per_step": enqueue_ms / args.steps, "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),

@@ -10,6 +10,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "nccl_shim.cuh"
+#include "p2p_allreduce.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -33,6 +34,7 @@ struct evc_dict {
   float* colsum = nullptr;   // A^T 1  (N)
   tc::DictOperands tc_ops;   // tensor-core operand copies + tensor maps (modes 1..3)
   evc_comm* comm = nullptr;  // exemplar sharding: all-reduce of partial A*H
+  p2p::State p2p;            // ... by our own kernel over NVLink peer memory when attached (else NCCL)
   // per-solve workspace, grow-only
   DevBuf WH, R, rowd, w0, active, num0, tcws;
   double* host_rows = nullptr;  // pinned mirror of rowd
@@ -48,9 +50,16 @@ namespace {
 
 thread_local double g_last_enqueue_ms = 0.0;
 
+// A*H of the current activations.  With the peer-memory all-reduce attached it lives in the IPC exchange buffer
+// (the reduced result lands there directly); otherwise in the handle's own workspace.
+inline float* wh_buf(evc_dict* d) { return d->p2p.attached ? d->p2p.recv() : d->WH.as<float>(); }
+
 int reserve_workspace(evc_dict* d, int T, int ldH, bool need_num0) {
   d->ldWH = round_up(d->F, 4);
   d->ldR = tc::k_pitch(d->F);
+  if (d->p2p.attached && T > d->p2p.t_max)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "T = %d exceeds the %d frames the peer-memory exchange buffer was sized for", T,
+                d->p2p.t_max);
   EVC_TRY(d->WH.reserve((size_t)T * d->ldWH * sizeof(float)));
   EVC_TRY(d->R.reserve((size_t)T * d->ldR * sizeof(float)));
   EVC_TRY(d->rowd.reserve((size_t)T * sizeof(double)));
@@ -75,17 +84,22 @@ int reserve_workspace(evc_dict* d, int T, int ldH, bool need_num0) {
 // WH (T, ldWH) = H (T,N) * A (N,F)         [first contraction; sklearn :554]
 int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH, bool target, cudaStream_t s,
                 const tc::RatioArgs* ra = nullptr) {
+  const bool sharded = d->comm && d->comm->world > 1;
+  // peer-memory all-reduce: the local partial goes to the send region, the sum arrives in the recv region (== WH)
+  const bool use_p2p = sharded && d->p2p.attached && WH == d->p2p.recv() && ldWH == d->ldWH;
+  float* local_out = use_p2p ? d->p2p.send() : WH;
   if (d->mode == EVC_MODE_FP32) {
     ProfScope ps(0, s);
     simt::EpiArgs e{};
-    e.C = WH; e.ldc = ldWH;
+    e.C = local_out; e.ldc = ldWH;
     EVC_TRY((simt::launch_gemm<simt::EPI_STORE, false>(T, d->F, d->N, H, ldH, target ? d->B : d->A, d->ldA, e, s)));
   } else {
-    EVC_TRY(tc::contract_wh(d->tc_ops, d->mode, H, ldH, T, WH, ldWH, target, &d->tcws, s, ra));
+    EVC_TRY(tc::contract_wh(d->tc_ops, d->mode, H, ldH, T, local_out, ldWH, target, &d->tcws, s, ra));
   }
-  if (d->comm && d->comm->world > 1) {
+  if (sharded) {
     ProfScope ps(3, s);  // exemplar sharding: the per-iteration exchange of the partial A*H
-    EVC_TRY(nccl::all_reduce_sum(d->comm->comm, WH, (size_t)T * ldWH, s));
+    if (use_p2p) EVC_TRY(p2p::all_reduce(&d->p2p, (size_t)T * ldWH, s));
+    else EVC_TRY(nccl::all_reduce_sum(d->comm->comm, WH, (size_t)T * ldWH, s));
   }
   return EVC_OK;
 }
@@ -98,7 +112,7 @@ int update_kl(evc_dict* d, const float* X, int ldX, int T, float* H, int ldH, fl
     {
       ProfScope ps(1, s);
       dim3 g(T, ceil_div(d->ldR, 256));
-      simt::ratio_kernel<<<g, 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, R, d->ldR, T, d->F, eps);
+      simt::ratio_kernel<<<g, 256, 0, s>>>(X, ldX, wh_buf(d), d->ldWH, R, d->ldR, T, d->F, eps);
       EVC_LAUNCH_CHECK();
     }
     ProfScope ps(2, s);
@@ -107,7 +121,7 @@ int update_kl(evc_dict* d, const float* X, int ldX, int T, float* H, int ldH, fl
     EVC_TRY((simt::launch_gemm<simt::EPI_MU_KL, true>(T, d->N, d->F, R, d->ldR, d->A, d->ldA, e, s)));
     return EVC_OK;
   }
-  return tc::update_kl(d->tc_ops, d->mode, X, ldX, T, d->WH.as<float>(), d->ldWH, R, d->ldR, H, ldH, d->colsum,
+  return tc::update_kl(d->tc_ops, d->mode, X, ldX, T, wh_buf(d), d->ldWH, R, d->ldR, H, ldH, d->colsum,
                        lam, eps, row_active, &d->tcws, s, ratio_done);
 }
 
@@ -118,10 +132,10 @@ int update_fro(evc_dict* d, int T, float* H, int ldH, const float* num0, float l
     ProfScope ps(2, s);
     simt::EpiArgs e{};
     e.C = H; e.ldc = ldH; e.X = num0; e.ldx = ldH; e.lam = lam; e.eps = eps; e.row_active = row_active;
-    EVC_TRY((simt::launch_gemm<simt::EPI_MU_FRO, true>(T, d->N, d->F, d->WH.as<float>(), d->ldWH, d->A, d->ldA, e, s)));
+    EVC_TRY((simt::launch_gemm<simt::EPI_MU_FRO, true>(T, d->N, d->F, wh_buf(d), d->ldWH, d->A, d->ldA, e, s)));
     return EVC_OK;
   }
-  return tc::update_fro(d->tc_ops, d->mode, T, d->WH.as<float>(), d->ldWH, d->R.as<float>(), d->ldR, H, ldH, num0,
+  return tc::update_fro(d->tc_ops, d->mode, T, wh_buf(d), d->ldWH, d->R.as<float>(), d->ldR, H, ldH, num0,
                         lam, eps, row_active, &d->tcws, s);
 }
 
@@ -139,10 +153,10 @@ int frob_numerator(evc_dict* d, const float* X, int ldX, int T, float* num0, int
 // Per-segment objective: err[u] = sqrt(2 * sum rows) (KL) or sqrt(sum rows) (Frobenius). Synchronises.
 int objective_segments(evc_dict* d, const float* X, int ldX, int T, const float* H, int ldH, int loss, float eps,
                        const std::vector<int>& seg, std::vector<double>& err, cudaStream_t s) {
-  EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, false, s));
+  EVC_TRY(contract_wh(d, H, ldH, T, wh_buf(d), d->ldWH, false, s));
   {
     ProfScope ps(3, s);
-    simt::objective_rows_kernel<<<ceil_div(T, 8), 256, 0, s>>>(X, ldX, d->WH.as<float>(), d->ldWH, T, d->F, eps, loss,
+    simt::objective_rows_kernel<<<ceil_div(T, 8), 256, 0, s>>>(X, ldX, wh_buf(d), d->ldWH, T, d->F, eps, loss,
                                                               d->rowd.as<double>());
     EVC_LAUNCH_CHECK();
   }
@@ -233,7 +247,7 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
     const unsigned char* mask = any_frozen ? d->active.as<unsigned char>() : nullptr;
     bool ratio_done = false;
     if (!wh_fresh) {
-      EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, false, s, fuse_ratio ? &ra : nullptr));
+      EVC_TRY(contract_wh(d, H, ldH, T, wh_buf(d), d->ldWH, false, s, fuse_ratio ? &ra : nullptr));
       ratio_done = fuse_ratio;
     }
     wh_fresh = false;
@@ -306,7 +320,7 @@ int evc_dict_destroy(evc_dict_t d) {
   cudaFree(d->A); cudaFree(d->B); cudaFree(d->colsum);
   d->tc_ops.release();
   d->WH.release(); d->R.release(); d->rowd.release(); d->w0.release(); d->active.release();
-  d->num0.release(); d->tcws.release(); d->prof.release();
+  d->num0.release(); d->tcws.release(); d->prof.release(); p2p::release(&d->p2p);
   if (g_prof == &d->prof) g_prof = nullptr;
   if (d->host_rows) cudaFreeHost(d->host_rows);
   if (d->host_w0) cudaFreeHost(d->host_w0);
@@ -408,8 +422,8 @@ static int product_impl(evc_dict_t d, const float* H, int ldH, int T, float* Y, 
   EVC_TRY(tc::check_alignment(d->mode, H, ldH));
   EVC_TRY(reserve_workspace(d, T, ldH, false));
   EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
-  EVC_TRY(contract_wh(d, H, ldH, T, d->WH.as<float>(), d->ldWH, target, s));
-  EVC_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldY * sizeof(float), d->WH.p, (size_t)d->ldWH * sizeof(float),
+  EVC_TRY(contract_wh(d, H, ldH, T, wh_buf(d), d->ldWH, target, s));
+  EVC_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldY * sizeof(float), wh_buf(d), (size_t)d->ldWH * sizeof(float),
                              (size_t)d->F * sizeof(float), T, cudaMemcpyDeviceToDevice, s));
   return EVC_OK;
 }
@@ -497,6 +511,18 @@ int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total) {
   d->comm = c;
   d->n_total = c ? n_total : d->N;
   return EVC_OK;
+}
+
+int evc_p2p_alloc(evc_dict_t d, int max_frames, char handle_out[64]) {
+  if (!d || !handle_out || max_frames < 1) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_p2p_alloc: bad argument");
+  return p2p::alloc_local(&d->p2p, max_frames, round_up(d->F, 4), handle_out);
+}
+
+int evc_p2p_attach(evc_dict_t d, const char* handles, int rank, int world) {
+  if (!d || !handles) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_p2p_attach: null argument");
+  if (!d->comm || d->comm->world != world || d->comm->rank != rank)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_p2p_attach: call evc_dict_attach_comm with the same rank/world first");
+  return p2p::attach(&d->p2p, handles, rank, world);
 }
 
 int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int* idx, const int* lo, const int* hi,

@@ -143,6 +143,22 @@ class ExemplarDictionary:
         check(L.evc_dict_attach_comm(self._h, self._comm, n_total))
         self.n_total = n_total
 
+    def p2p_alloc(self, max_frames: int) -> bytes:
+        """Allocate this rank's peer-memory exchange buffer (for up to max_frames frames); returns its CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().evc_p2p_alloc(self._h, int(max_frames), buf))
+        return buf.raw
+
+    def p2p_attach(self, handles: Sequence[bytes], rank: int, world: int):
+        """Map the peers' exchange buffers: from now on the partial A*H is summed by libevc_b200's own kernel over
+        NVLink peer memory instead of ncclAllReduce."""
+        blob = b"".join(handles)
+        if len(blob) != 64 * world:
+            raise ValueError("expected one 64-byte IPC handle per rank")
+        with torch.cuda.device(self.device):
+            check(_lib.lib().evc_p2p_attach(self._h, blob, rank, world))
+
     # -- the hot path ---------------------------------------------------------------------------------
     def _params(self, beta_loss, tol, max_iter, lam, lambda_step, init_given, check_every, epsilon) -> SolveParams:
         p = SolveParams()

@@ -88,7 +88,7 @@ def broadcast_unique_id(make_id: Callable[[], bytes], *, group=None, src: int = 
 
 
 def make_exemplar_sharded(A_rows: Callable[[int, int], np.ndarray], B_rows: Optional[Callable[[int, int], np.ndarray]],
-                          N: int, *, mode: str = "3xtf32", group=None):
+                          N: int, *, mode: str = "3xtf32", group=None, p2p: bool = True, max_frames: int = 4096):
     """Build this rank's shard of an N-exemplar dictionary.  `A_rows(n0, n1)` / `B_rows(n0, n1)` return the
     rows the rank owns (so a 200k-exemplar dictionary is never materialised whole on one host).  The
     returned ExemplarDictionary all-reduces partial A*H inside solve / convert / objective."""
@@ -112,4 +112,31 @@ def make_exemplar_sharded(A_rows: Callable[[int, int], np.ndarray], B_rows: Opti
     uid = broadcast_unique_id(make_id, group=group)
     d.attach_comm(uid, rank, world, N)
     d.n_begin, d.n_end = n0, n1
+    d.all_reduce = "nccl"
+    if p2p and 2 <= world <= 8:
+        # our own all-reduce kernel over NVLink peer memory (CUDA IPC between the per-GPU processes of one node);
+        # every rank must succeed, otherwise all of them stay on NCCL
+        try:
+            handle, err = d.p2p_alloc(max_frames), None
+        except Exception as e:  # pragma: no cover - depends on the container's IPC permissions
+            handle, err = None, repr(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        if all(h is not None for h in handles):
+            try:
+                d.p2p_attach(handles, rank, world)
+                ok = True
+            except Exception as e:  # pragma: no cover
+                ok, err = False, repr(e)
+        else:
+            ok = False
+        oks = [None] * world
+        dist.all_gather_object(oks, ok, group=group)
+        if all(oks):
+            d.all_reduce = "p2p"
+        elif ok:
+            raise RuntimeError("peer-memory all-reduce attached on this rank but not on all ranks: " + repr(oks))
+        elif err and rank == 0:
+            import warnings
+            warnings.warn("peer-memory all-reduce unavailable, using NCCL: " + err)
     return d

@@ -168,6 +168,15 @@ int evc_dict_attach_comm(evc_dict_t d, evc_comm_t c, int n_total);
 int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int* idx, const int* lo, const int* hi,
                      int n_out, int context, float* out, int ld_out, void* stream);
 
+/*
+ * Optional: replace the NCCL all-reduce of the exemplar-sharded path by libevc_b200's own kernel over NVLink peer
+ * memory (one node, 2..8 ranks, one process per GPU).  Every rank calls evc_p2p_alloc (allocates the exchange buffer
+ * for up to max_frames frames and returns a 64-byte CUDA IPC handle), the handles of all ranks are exchanged by the
+ * host (rank-major, world*64 bytes) and passed to evc_p2p_attach.  evc_dict_attach_comm must have been called first.
+ */
+int evc_p2p_alloc(evc_dict_t d, int max_frames, char handle_out[64]);
+int evc_p2p_attach(evc_dict_t d, const char* handles, int rank, int world);
+
 /* Diagnostics: host milliseconds the last evc_solve* on this thread spent ENQUEUEING its iteration loop (if this
  * approaches the device time of the loop, the GPU is waiting for the host). */
 double evc_last_enqueue_ms(void);

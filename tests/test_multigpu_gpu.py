@@ -24,15 +24,28 @@ def _worker(rank, world, port, mode):
     # ---- exemplar sharding: N = 1000 rows split at a 128-row boundary, 513 bins (leftover row path too)
     X, A, B = o.gen(71, 513, 1000, 40)
     W_ref, n_ref, obj_ref = o.kl_mu(X, A, tol=1e-4, max_iter=40)
-    d = sharding.make_exemplar_sharded(lambda a, b: A[a:b], lambda a, b: B[a:b], 1000, mode=mode)
-    act = d.solve(X, tol=1e-4, max_iter=40)
-    H = d.to_host(act.H).astype(np.float64)
-    Y = d.to_host(d.convert(act.H)).astype(np.float64)
-    assert act.n_iter == n_ref
-    assert np.linalg.norm(H - W_ref[:, d.n_begin:d.n_end]) / np.linalg.norm(W_ref[:, d.n_begin:d.n_end]) < 1e-3
-    assert np.linalg.norm(Y - W_ref @ B) / np.linalg.norm(W_ref @ B) < 1e-3      # Y is all-reduced: complete on every rank
-    assert abs(act.objective - obj_ref) / obj_ref < 1e-4
-    d.close()
+    results = {}
+    for p2p in (True, False):      # libevc_b200's own all-reduce over NVLink peer memory, then ncclAllReduce
+        d = sharding.make_exemplar_sharded(lambda a, b: A[a:b], lambda a, b: B[a:b], 1000, mode=mode, p2p=p2p,
+                                           max_frames=64)
+        if p2p and d.all_reduce != "p2p" and rank == 0:
+            print("peer-memory all-reduce not available here; NCCL used for both passes")
+        act = d.solve(X, tol=1e-4, max_iter=40)
+        H = d.to_host(act.H).astype(np.float64)
+        Y = d.to_host(d.convert(act.H)).astype(np.float64)
+        assert act.n_iter == n_ref
+        assert np.linalg.norm(H - W_ref[:, d.n_begin:d.n_end]) / np.linalg.norm(W_ref[:, d.n_begin:d.n_end]) < 1e-3
+        assert np.linalg.norm(Y - W_ref @ B) / np.linalg.norm(W_ref @ B) < 1e-3   # Y is all-reduced: complete on every rank
+        assert abs(act.objective - obj_ref) / obj_ref < 1e-4
+        results[d.all_reduce] = (H, Y, act.objective)
+        with pytest.raises(ValueError):
+            if d.all_reduce == "p2p":
+                d.solve(np.concatenate([X, X]), tol=0.0, max_iter=1)      # more frames than the exchange buffer holds
+            else:
+                raise ValueError("n/a")
+        d.close()
+    if len(results) == 2:      # same partials, both sums in a fixed order: the two exchanges agree to rounding
+        assert np.allclose(results["p2p"][1], results["nccl"][1], rtol=1e-5, atol=0)
 
     # ---- utterance sharding: every rank holds the whole dictionary, converts its own utterances
     rng = np.random.default_rng(5)
