@@ -715,7 +715,16 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
     if (f0 + 4 <= F_main && (f0 >= f_last || f0 + 4 <= f_last)) {
       const int n = (f0 >= f_last) ? S_last : S;  // columns of the last row group have their own split count
       const float* p0 = P + (size_t)t * ldp + f0;
-      for (int k = 0; k < n; ++k) {
+      // batches of 6 independent 16-byte loads in flight, summed in split order (deterministic)
+      int k = 0;
+      for (; k + 6 <= n; k += 6) {
+        float4 v[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] = *reinterpret_cast<const float4*>(p0 + (size_t)(k + q) * T * ldp);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { s[0] += v[q].x; s[1] += v[q].y; s[2] += v[q].z; s[3] += v[q].w; }
+      }
+      for (; k < n; ++k) {
         const float4 v = *reinterpret_cast<const float4*>(p0 + (size_t)k * T * ldp);
         s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       }
