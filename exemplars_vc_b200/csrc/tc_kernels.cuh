@@ -135,7 +135,7 @@ constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = 4;
 // tcgen05.mma.cta_group::2 with M = 256 (128 dictionary rows per CTA) and the frame (N) operand split in halves
 // between the two CTAs' shared memories, which halves the per-SM shared-memory reads of the frame operand
 // (the 3xTF32 main loop of the 1-CTA version is shared-memory-bandwidth bound).
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, bool kStageH, int kCG>
+template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, bool kStageH, int kCG, bool kStageQ = false>
 struct TileCfg {
   static constexpr int kRowBytes = kBlockK * 4;
   static constexpr int kMTileBytes = 128 * kRowBytes;              // this CTA's 128 rows of one dictionary sub-tile
@@ -148,6 +148,9 @@ struct TileCfg {
   static constexpr int kOffMlo = kMBytes;
   static constexpr int kOffN = kCopies * kMBytes;
   static constexpr int kOffNlo = kOffN + kNTileBytes;
+  // Frobenius also stages the cached numerator X A^T next to H: half as many, twice as large buffers
+  static constexpr int kHBufsUsed = kStageQ ? kHBufs / 2 : kHBufs;
+  static constexpr int kHBufStride = kStageQ ? 2 * kHBufBytes : kHBufBytes;
   static constexpr int kHBytes = kStageH ? kHBufs * kHBufBytes : 0;
   static constexpr int kStagesRaw = (kSmemBudget - kHBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -208,11 +211,14 @@ __device__ __forceinline__ void split_stage(uint8_t* stage, int lane, int part) 
 }
 
 template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
-__global__ void __launch_bounds__((TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL, kCG>::kThreads), 1)
+__global__ void __launch_bounds__(
+    (TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO, kCG, kEpi == TEPI_MU_FRO>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
-               const __grid_constant__ CUtensorMap tmH, const GemmParams p) {
-  constexpr bool kStageH = (kEpi == TEPI_MU_KL);
-  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kStageH, kCG>;
+               const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmQ, const GemmParams p) {
+  constexpr bool kFro = (kEpi == TEPI_MU_FRO);
+  constexpr bool kStageH = (kEpi == TEPI_MU_KL) || kFro;
+  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kStageH, kCG, kFro>;
+  constexpr int kHB = Cfg::kHBufsUsed;  // chunk buffers in use
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
   constexpr uint32_t kIdesc = make_idesc(kFmtTF32, 128 * kCG, kBlockT);
@@ -242,6 +248,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     tma_prefetch_desc(&tmM);
     tma_prefetch_desc(&tmN);
     if (kStageH) tma_prefetch_desc(&tmH);
+    if (kFro) tma_prefetch_desc(&tmQ);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), 1);
       mbar_init(smem_u32(&bar_ready[i]), Cfg::kReadyArrivals * kCG);
@@ -432,12 +439,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = 0; c < nch; ++c) {
-          const int seq = hbase + c, b = seq % kHBufs;
-          const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
+          const int seq = hbase + c, b = seq % kHB;
+          const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hempty[b]), ph ^ 1u);
           const uint32_t full = smem_u32(&bar_hfull[b]);
-          mbar_arrive_expect_tx(full, (uint32_t)kHBufBytes);
-          tma_load_2d(ring + Cfg::kOffH + b * kHBufBytes, &tmH, n0, t0 + c * kHChunkT, full, kEvictFirst);
+          mbar_arrive_expect_tx(full, (uint32_t)Cfg::kHBufStride);
+          tma_load_2d(ring + Cfg::kOffH + b * Cfg::kHBufStride, &tmH, n0, t0 + c * kHChunkT, full, kEvictFirst);
+          if (kFro)
+            tma_load_2d(ring + Cfg::kOffH + b * Cfg::kHBufStride + kHBufBytes, &tmQ, n0, t0 + c * kHChunkT, full, kEvictFirst);
         }
         hbase += nch;
       }
@@ -451,10 +460,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = 0; c < nch; ++c) {
-          const int seq = hbase + c, b = seq % kHBufs;
-          const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
+          const int seq = hbase + c, b = seq % kHB;
+          const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hready[b]), ph);
-          tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * kHBufBytes);
+          tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * Cfg::kHBufStride);
           tma_store_commit();
           tma_store_wait_read();
           mbar_arrive(smem_u32(&bar_hempty[b]));
@@ -547,31 +556,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       if (kStageH) {
         // ---- fused multiplicative update through the shared-memory H chunks ----
         const int m = m_group * Cfg::kRowsPerSub + (int)rank * 128 + quarter * 32 + lane;
-        float den = ((m < p.M_total) ? p.colsum[m] : 1.f) + p.lam;
+        float den = ((m < p.M_total && !kFro) ? p.colsum[m] : 1.f) + p.lam;
         if (den == 0.f) den = p.eps;
         const float inv_den = __frcp_rn(den);
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = half; c < nch; c += 2) {
-          const int seq = hbase + c, b = seq % kHBufs;
-          const uint32_t ph = (uint32_t)(seq / kHBufs) & 1u;
+          const int seq = hbase + c, b = seq % kHB;
+          const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockT + c * 32), v);
           c0 = clock64();
           mbar_wait(smem_u32(&bar_hfull[b]), ph);
           c_hfull += clock64() - c0;
-          float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * kHBufBytes) + quarter * 32 + lane;
+          float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * Cfg::kHBufStride) + quarter * 32 + lane;
           float h[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) h[j] = hb[j * 128];
           tmem_ld_wait();
-          if (p.row_active == nullptr) {
+          const int tbm = t0 + c * 32;
+          if (kFro) {
+            // Frobenius: H <- H * (X A^T) / (A^T (A H) + lambda); the numerator chunk sits behind the H chunk
+            const float* qb = hb + kHBufBytes / 4;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (p.row_active == nullptr || (tbm + j < p.T && p.row_active[tbm + j])) {
+                float dn = __uint_as_float(v[j]) + p.lam;
+                if (dn == 0.f) dn = p.eps;
+                h[j] = h[j] * __fdividef(qb[j * 128], dn);
+              }
+            }
+          } else if (p.row_active == nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
           } else {
-            const int tb = t0 + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (tb + j < p.T && p.row_active[tb + j]) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
+              if (tbm + j < p.T && p.row_active[tbm + j]) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
           }
           if (p.direct_store) {
             // registers -> global, 128 B per warp per frame; the chunk buffer is free as soon as it was read
@@ -633,18 +653,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (m_ok && tb + j < p.T) o[(size_t)j * p.ld_out] = __uint_as_float(v[j]);
-            }
-          } else {  // TEPI_MU_FRO (register path)
-            float* o = p.out + (size_t)tb * p.ld_out + m;
-            const float* q = p.num0 + (size_t)tb * p.ld_out + m;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool ok = m_ok && (tb + j < p.T) && (!p.row_active || p.row_active[tb + j]);
-              if (ok) {
-                float dn = __uint_as_float(v[j]) + p.lam;
-                if (dn == 0.f) dn = p.eps;
-                o[(size_t)j * p.ld_out] = o[(size_t)j * p.ld_out] * __fdividef(q[(size_t)j * p.ld_out], dn);
-              }
             }
           }
         }
@@ -874,9 +882,9 @@ inline bool use_pdl() {
 }
 
 template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
-inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const GemmParams& p,
-                     cudaStream_t s) {
-  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL, kCG>;
+inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const CUtensorMap& tmQ,
+                     const GemmParams& p, cudaStream_t s) {
+  using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO, kCG, kEpi == TEPI_MU_FRO>;
   auto kern = tc_gemm_kernel<kMTiles, kBlockT, kBlockK, kSplit3, kEpi, kCG>;
   static bool configured = false;
   if (!configured) {
@@ -912,7 +920,7 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
     EVC_CUDA(cudaMemsetAsync(dbuf, 0, 8 * sizeof(long long) * grid * 2, s));
     q.dbg_cycles = dbuf;
   }
-  EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, q));
+  EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, q));
   EVC_LAUNCH_CHECK();
   if (timing && prints < 6) {
     std::vector<long long> h((size_t)grid * 16);
@@ -1077,7 +1085,7 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   p.out = partials; p.ld_out = pl.ldp;
   {
     ProfScope ps(0, s);
-    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL, kCG>(target ? o.tmBT : o.tmAT, tmH, tmH, p, s)));
+    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL, kCG>(target ? o.tmBT : o.tmAT, tmH, tmH, tmH, p, s)));
   }
   // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
   const bool from_partials = o.n_left > 0 && !target && o.left_valid;
@@ -1137,10 +1145,11 @@ inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmPar
   // neighbouring CTAs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
   p.m_fastest = getenv("EVC_T_FASTEST") ? 0 : 1;
   p.direct_store = getenv("EVC_DIRECT_STORE") ? 1 : 0;
-  CUtensorMap tmHc = tmR;  // only the fused KL update stages H through shared memory
-  if (kEpi == TEPI_MU_KL) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
+  CUtensorMap tmHc = tmR, tmQc = tmR;  // the fused updates stage H (and the Frobenius numerator) through shared memory
+  if (kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
+  if (kEpi == TEPI_MU_FRO) EVC_TRY(make_tmap(&tmQc, p.num0, T, o.N, p.ld_out, 128, kHChunkT, false));
   ProfScope ps(2, s);
-  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi, kCG>(o.tmA, tmR, tmHc, p, s);
+  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi, kCG>(o.tmA, tmR, tmHc, tmQc, p, s);
 }
 
 template <bool kSplit3, int kEpi>
@@ -1171,10 +1180,16 @@ inline int update_fro(DictOperands& o, int mode, int T, const float* WH, int ldW
                       const float* num0, float lam, float eps, const unsigned char* row_active, DevBuf* ws,
                       cudaStream_t s) {
   EVC_TRY(launch_ratio(nullptr, 0, WH, ldWH, R, ldR, T, o.F, eps, 1, s));
-  o.left_valid = false;
   GemmParams p{};
   p.out = H; p.ld_out = ldH;
   p.num0 = num0; p.lam = lam; p.eps = eps; p.row_active = row_active;
+  if (o.n_left > 0) {
+    const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
+    const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
+    p.left_a = o.AT + (size_t)o.F_main * o.ldN; p.left_lda = o.ldN; p.n_left = o.n_left;
+    p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T); p.left_rows = left_rows(o);
+    o.left_valid = true;
+  }
   if (mode == EVC_MODE_3XTF32) return contract2_t<true, TEPI_MU_FRO>(o, T, R, ldR, p, s);
   return contract2_t<false, TEPI_MU_FRO>(o, T, R, ldR, p, s);
 }
