@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
+    ap.add_argument("--mode", default="3xtf32", choices=["3xtf32", "tf32", "bf16", "fp32"])
     ap.add_argument("--workload", default="single_utterance_20k")
     ap.add_argument("--iterations", type=int, default=None, help="override the workload's iteration count")
     ap.add_argument("--ref-sample-iters", type=int, default=5)
@@ -281,7 +281,7 @@ def main():
         flop = 2.0 * wl.T * wl.F * n_local
         achieved = flop / per_launch_s / 1e12 if per_launch_s > 0 else 0.0
         passes = 3 if args.mode == "3xtf32" else 1
-        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        tf32_peak = peaks["bf16_tflops_sustained"] / (1.0 if args.mode == "bf16" else 2.0)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -292,7 +292,8 @@ def main():
         roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<contraction 2 + MU epilogue>" if args.mode != "fp32"
                     else "simt gemm_kernel<MU epilogue>", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": achieved / tf32_peak, "traffic": traffic,
-                    "peak_source": "dense TF32 = 1/2 of bf16_tflops_sustained, " + peaks["_source"],
+                    "peak_source": ("dense BF16 = bf16_tflops_sustained, " if args.mode == "bf16" else
+                                    "dense TF32 = 1/2 of bf16_tflops_sustained, ") + peaks["_source"],
                     "executed_tflops": achieved * passes, "executed_frac": achieved * passes / tf32_peak,
                     "mma_passes_per_product": passes,
                     "us_per_launch": per_launch_s * 1e6,
@@ -303,7 +304,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if exemplar_sharded else "weak", "vs_baseline": None,
-                "dtype": {"3xtf32": "tf32x3 (fp32-accurate)", "tf32": "tf32", "fp32": "f32"}[args.mode],
+                "dtype": {"3xtf32": "tf32x3 (fp32-accurate)", "tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.mode],
                 "data": "synthetic",
                 "config": {"workload": wl.name, "F": wl.F, "N": wl.N, "T": wl.T, "iterations": wl.iterations,
                            "mode": args.mode, "sharding": ("exemplar" if exemplar_sharded else "utterance") if world > 1 else "none",

@@ -16,9 +16,16 @@
 // lo = x - hi (exact in fp32), written next to it in shared memory by split warps;
 // D += M_lo*N_hi + M_hi*N_lo + M_hi*N_hi, dropping lo*lo (2^-22 relative).  HBM and L2 only ever carry one
 // fp32 copy of each operand.
+//
+// BF16 fast mode (kBf16): the same kernel with tcgen05.mma.kind::f16 on bf16 operand copies -- the dictionary is
+// converted once, the ratio is emitted in bf16 by the reduction pass, and the fused update writes a bf16 shadow of
+// the activations next to the fp32 master copy (the multiplicative update itself stays fp32).  A K-block is still
+// one 128-byte swizzle row, i.e. 64 bf16 elements, and one MMA still advances 32 bytes of K (16 elements), so the
+// shared-memory layout, descriptors and barrier protocol are unchanged.
 #pragma once
 #include "evc_common.cuh"
 #include "umma.cuh"
+#include <cuda_bf16.h>
 #include <algorithm>
 #include <cstdlib>
 
@@ -47,6 +54,8 @@ struct GemmParams {
   int m_fastest;  // work-item order: 1 = consecutive CTAs take consecutive dictionary-row groups of one frame tile
   float* out;    // PARTIAL: [split][t][m] with pitch ld_out;  MU_*: the activations H (T, ld_out)
   int ld_out;
+  __nv_bfloat16* out16;  // BF16 mode, MU_*: bf16 shadow of H (T, ld_out16), the K operand of the next contraction 1
+  int ld_out16;
   const float* colsum;
   const float* num0;  // MU_FRO: cached numerator X A^T, same pitch as H
   float lam, eps;
@@ -210,7 +219,7 @@ __device__ __forceinline__ void split_stage(uint8_t* stage, int lane, int part) 
   split_region<Cfg>(stage + Cfg::kOffN, stage + Cfg::kOffNlo, Cfg::kNTileBytes, lane, part);
 }
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
+template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG, bool kBf16 = false>
 __global__ void __launch_bounds__(
     (TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO, kCG, kEpi == TEPI_MU_FRO>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
@@ -221,7 +230,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   constexpr int kHB = Cfg::kHBufsUsed;  // chunk buffers in use
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
-  constexpr uint32_t kIdesc = make_idesc(kFmtTF32, 128 * kCG, kBlockT);
+  static_assert(!(kBf16 && kSplit3), "the hi/lo split belongs to the TF32 path");
+  constexpr uint32_t kFmt = kBf16 ? kFmtBF16 : kFmtTF32;
+  constexpr int kKE = kBf16 ? 2 * kBlockK : kBlockK;  // K elements per K-block (one swizzle row)
+  constexpr int kKStep = kBf16 ? 16 : 8;              // K elements per MMA (32 bytes either way)
+  constexpr uint32_t kIdesc = make_idesc(kFmt, 128 * kCG, kBlockT);
   // does the MMA warp wait on the "ready" barrier (split and/or pair) or directly on the TMA barrier?
   constexpr bool kUseReady = kSplit3 || kCG == 2;
 
@@ -316,7 +329,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           while (use_la && la_valid && la_count < issued + kAhead) {
             if (la_count >= issued + kStages) {  // (the first kStages blocks are about to be loaded anyway)
-              const int kc = la_kb * kBlockK;
+              const int kc = la_kb * kKE;
 #pragma unroll
               for (int i = 0; i < kMTiles; ++i)
                 if (la_m0 + i * Cfg::kRowsPerSub < p.M_total) tma_prefetch_l2_2d(&tmM, kc, la_m0 + i * Cfg::kRowsPerSub);
@@ -347,7 +360,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           mbar_arrive_expect_tx(full, (uint32_t)Cfg::kLoadBytes);
           if (p.dbg_cycles) dbg_t_issue[stage] = clock64();
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
-          const int kc = kb * kBlockK;
+          const int kc = kb * kKE;
           // (sub-tiles past M_total are still loaded: TMA zero-fills them and the byte count stays constant)
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i)
@@ -372,7 +385,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const WorkItem w = decode_item(p, item, kBlockT);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles);
         const int kb0 = w.kb0, kb1 = w.kb1;
-        const uint32_t idesc = (w.t_cols == kBlockT) ? kIdesc : make_idesc(kFmtTF32, 128 * kCG, (uint32_t)w.t_cols);
+        const uint32_t idesc = (w.t_cols == kBlockT) ? kIdesc : make_idesc(kFmt, 128 * kCG, (uint32_t)w.t_cols);
         long long c0 = clock64();
         if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
         else mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
@@ -387,8 +400,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
           const uint32_t nbase = sbase + Cfg::kOffN;
-          const int kvalid = min(kBlockK, p.K - kb * kBlockK);
-          const int ksteps = (kvalid + 7) >> 3;
+          const int kvalid = min(kKE, p.K - kb * kKE);
+          const int ksteps = (kvalid + kKStep - 1) / kKStep;
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i) {
             if (m0 + i * Cfg::kRowsPerSub >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
@@ -412,8 +425,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
                   mma_tf32(d, a_hi, b_hi, idesc, 1u);
                 }
               } else {
-                if (kCG == 2) mma_tf32_2cta(d, a_hi, b_hi, idesc, accum);
-                else mma_tf32(d, a_hi, b_hi, idesc, accum);
+                mma_issue<kBf16, kCG>(d, a_hi, b_hi, idesc, accum);
               }
             }
           }
@@ -593,6 +605,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (tbm + j < p.T && p.row_active[tbm + j]) h[j] = h[j] * (__uint_as_float(v[j]) * inv_den);
           }
+          if (kBf16 && p.out16 != nullptr && m < p.M_total && !(p.debug_flags & 8)) {
+            // bf16 shadow of the updated activations: 64 contiguous bytes per warp per frame, straight from registers
+            __nv_bfloat16* o16 = p.out16 + (size_t)tbm * p.ld_out16 + m;
+            const int rows = min(32, p.T - tbm);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < rows) o16[(size_t)j * p.ld_out16] = __float2bfloat16_rn(h[j]);
+          }
           if (p.direct_store) {
             // registers -> global, 128 B per warp per frame; the chunk buffer is free as soon as it was read
             __syncwarp();
@@ -695,7 +715,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 __global__ void __launch_bounds__(128)
 reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
                        float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
-                       int left_ld, const float* __restrict__ X, int ldx, float* __restrict__ R, int ldr, float eps) {
+                       int left_ld, const float* __restrict__ X, int ldx, float* __restrict__ R, int ldr, float eps,
+                       __nv_bfloat16* __restrict__ R16, int ldr16) {
   // one block per frame; a thread owns groups of 4 consecutive columns (16-byte loads of the partials)
   __shared__ float s_left[8];
   __shared__ float s_warp[4];
@@ -716,7 +737,7 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
       __syncthreads();
     }
   }
-  const int cols = max(ldwh, R ? ldr : 0);
+  const int cols = max(ldwh, max(R ? ldr : 0, R16 ? ldr16 : 0));
   for (int f0 = threadIdx.x * 4; f0 < cols; f0 += blockDim.x * 4) {
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     bool have[4] = {false, false, false, false};
@@ -755,8 +776,11 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
     for (int j = 0; j < 4; ++j) {
       const int f = f0 + j;
       if (f < ldwh && (have[j] || f >= F)) WH[(size_t)t * ldwh + f] = s[j];
-      if (R && f < ldr)
-        R[(size_t)t * ldr + f] = (have[j] && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s[j], eps)) : 0.f;
+      if ((R && f < ldr) || (R16 && f < ldr16)) {
+        const float r = (have[j] && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s[j], eps)) : 0.f;
+        if (R && f < ldr) R[(size_t)t * ldr + f] = r;
+        if (R16 && f < ldr16) R16[(size_t)t * ldr16 + f] = __float2bfloat16_rn(r);
+      }
     }
   }
 }
@@ -795,17 +819,44 @@ leftover_rows_kernel(const float* __restrict__ H, int ldh, int T, int N, const f
 
 // R = X / max(WH, eps) with zeroed pad columns; `copy` = 1 stores WH itself (Frobenius: the second
 // contraction multiplies A^T with A H; also used to stage X for the Frobenius numerator).
+// With `R16` the result is stored as bf16 (pitch ldr16) instead: the K operand of the BF16 mode.
 __global__ void ratio_pad_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ WH, int ldwh,
-                                 float* __restrict__ R, int ldr, int T, int F, float eps, int copy) {
+                                 float* __restrict__ R, int ldr, int T, int F, float eps, int copy,
+                                 __nv_bfloat16* __restrict__ R16, int ldr16) {
   const int f = blockIdx.y * blockDim.x + threadIdx.x;
   const int t = blockIdx.x;
-  if (t >= T || f >= ldr) return;
+  if (t >= T || f >= (R16 ? ldr16 : ldr)) return;
   float r = 0.f;
   if (f < F) {
     const float wh = WH[(size_t)t * ldwh + f];
     r = copy ? wh : __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(wh, eps));
   }
-  R[(size_t)t * ldr + f] = r;
+  if (R16) R16[(size_t)t * ldr16 + f] = __float2bfloat16_rn(r);
+  else R[(size_t)t * ldr + f] = r;
+}
+
+// dst (rows, ldd) bf16 = src (rows, lds) fp32, round to nearest even; pad columns [cols, ldd) are zeroed.
+__global__ void to_bf16_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd,
+                               int rows, int cols) {
+  const int r = blockIdx.x;
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (r >= rows || c0 >= ldd) return;
+  const float* sp = src + (size_t)r * lds;
+  __nv_bfloat16* dp = dst + (size_t)r * ldd;
+  if (c0 + 4 <= cols && (lds & 3) == 0 && (ldd & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0) {
+    const float4 v = *reinterpret_cast<const float4*>(sp + c0);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dp + c0) = pk;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      if (c < ldd) dp[c] = __float2bfloat16_rn(c < cols ? sp[c] : 0.f);
+    }
+  }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -828,26 +879,35 @@ inline int get_encode(PFN_encodeTiled* out) {
   return EVC_OK;
 }
 
-// Row-major fp32 matrix (rows, cols) with pitch ld floats; box = box_rows x box_cols, box_cols*4 in {64,128}.
-inline int make_tmap(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows,
-                     bool swizzle = true) {
+// Row-major matrix (rows, cols) of `esize`-byte elements (4: fp32, 2: bf16) with pitch ld elements;
+// box = box_rows x box_cols elements, box_cols*esize in {64,128} when swizzled.
+inline int make_tmap_any(CUtensorMap* m, const void* base, int esize, int rows, int cols, int ld, int box_cols,
+                         int box_rows, bool swizzle) {
   PFN_encodeTiled enc;
   EVC_TRY(get_encode(&enc));
-  if (((uintptr_t)base & 15) || (ld & 3))
-    return fail(EVC_ERR_INVALID_ARGUMENT, "tensor-core modes need 16-byte aligned matrices with a pitch multiple of 4 floats");
+  if (((uintptr_t)base & 15) || (((size_t)ld * esize) & 15))
+    return fail(EVC_ERR_INVALID_ARGUMENT, "tensor-core modes need 16-byte aligned matrices with a 16-byte multiple pitch");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle sw = !swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE
-                                : (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                : (box_cols * esize == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(EVC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box=%dx%d", (int)r, rows, cols,
                 ld, box_rows, box_cols);
   return EVC_OK;
+}
+inline int make_tmap(CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_cols, int box_rows,
+                     bool swizzle = true) {
+  return make_tmap_any(m, base, 4, rows, cols, ld, box_cols, box_rows, swizzle);
+}
+inline int make_tmap16(CUtensorMap* m, const __nv_bfloat16* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+  return make_tmap_any(m, base, 2, rows, cols, ld, box_cols, box_rows, true);
 }
 
 inline int num_sms() {
@@ -881,11 +941,11 @@ inline bool use_pdl() {
   return on;
 }
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG>
+template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG, bool kBf16 = false>
 inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const CUtensorMap& tmQ,
                      const GemmParams& p, cudaStream_t s) {
   using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO, kCG, kEpi == TEPI_MU_FRO>;
-  auto kern = tc_gemm_kernel<kMTiles, kBlockT, kBlockK, kSplit3, kEpi, kCG>;
+  auto kern = tc_gemm_kernel<kMTiles, kBlockT, kBlockK, kSplit3, kEpi, kCG, kBf16>;
   static bool configured = false;
   if (!configured) {
     EVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -928,9 +988,9 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
     EVC_CUDA(cudaMemcpy(h.data(), dbuf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     double a[8] = {0}; int nl = 0;
     for (int b = 0; b < grid; b += kCG) { for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)b * 8 + k]; ++nl; }
-    fprintf(stderr, "[evc timing] kernel<%d,%d,%d,%d,%d,cg%d> grid %d (leaders avg, cycles): mma loop %.0f (wait acc_empty %.0f, wait ready %.0f) | "
+    fprintf(stderr, "[evc timing] kernel<%d,%d,%d,%d,%d,cg%d%s> grid %d (leaders avg, cycles): mma loop %.0f (wait acc_empty %.0f, wait ready %.0f) | "
             "producer loop %.0f (wait empty %.0f) | epilogue warp loop %.0f (wait acc_full %.0f, wait hfull %.0f)\n",
-            kMTiles, kBlockT, kBlockK, (int)kSplit3, kEpi, kCG, grid, a[0] / nl, a[1] / nl, a[2] / nl, a[3] / nl, a[4] / nl,
+            kMTiles, kBlockT, kBlockK, (int)kSplit3, kEpi, kCG, kBf16 ? ",bf16" : "", grid, a[0] / nl, a[1] / nl, a[2] / nl, a[3] / nl, a[4] / nl,
             a[5] / nl, a[6] / nl, a[7] / nl);
     double tma = 0, spl = 0, cnt = 0;
     for (int b = 0; b < grid; ++b) { tma += (double)h[(size_t)(grid + b) * 8]; spl += (double)h[(size_t)(grid + b) * 8 + 1]; cnt += (double)h[(size_t)(grid + b) * 8 + 2]; }
@@ -945,6 +1005,10 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
 constexpr int kC1MTiles = 2, kC1BlockT = 256;  // contraction 1 / conversion: 256 dictionary rows x 256 frames, split-K
 constexpr int kC2MTiles = 1, kC2BlockT = 256;  // contraction 2: 128 exemplars x 256 frames, 2 accumulator stages
 constexpr int kBlockK3 = 16, kBlockK1 = 32;
+// K elements per K-block of a mode (BF16: a 128-byte swizzle row holds 64 elements)
+inline int bk_elems(int mode) {
+  return mode == EVC_MODE_3XTF32 ? kBlockK3 : mode == EVC_MODE_BF16 ? 2 * kBlockK1 : kBlockK1;
+}
 
 // CTA group of the MMAs: 2 (CTA pairs, default) or 1 (EVC_CTA_GROUP=1: single-CTA kernels, kept for A/B runs).
 inline int cta_group() {
@@ -963,15 +1027,29 @@ struct DictOperands {
   CUtensorMap tmA, tmAT, tmBT;
   int F_main = 0, n_left = 0;  // contraction 1 runs rows [0, F_main) on the tensor cores; n_left = F - F_main <= 8
   bool left_valid = false;     // the workspace holds leftover partials of the CURRENT activations
+  // BF16 mode: bf16 copies of the three operands, and the per-solve bf16 shadows of H and of the ratio
+  int ldA16 = 0, ldN16 = 0;
+  __nv_bfloat16 *A16 = nullptr, *AT16 = nullptr, *BT16 = nullptr;
+  CUtensorMap tmA16, tmAT16, tmBT16;
+  DevBuf h16, r16;
   void release() {
-    cudaFree(AT); cudaFree(BT);
+    cudaFree(AT); cudaFree(BT); cudaFree(A16); cudaFree(AT16); cudaFree(BT16);
     AT = BT = nullptr;
+    A16 = AT16 = BT16 = nullptr;
+    h16.release(); r16.release();
   }
 };
 
+inline int launch_to_bf16(const float* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols, cudaStream_t s) {
+  if (rows <= 0) return EVC_OK;
+  dim3 g(rows, ceil_div(ldd, 4 * 256));
+  to_bf16_kernel<<<g, 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
+  EVC_LAUNCH_CHECK();
+  return EVC_OK;
+}
+
 inline int build_operands(DictOperands* o, int mode, const float* A, const float* B, int ldA, int F, int N, cudaStream_t s) {
-  if (mode == EVC_MODE_BF16) return fail(EVC_ERR_UNSUPPORTED, "EVC_MODE_BF16 is not implemented yet");
-  const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
+  const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;  // (fp32 maps; BF16 builds its own below)
   o->F = F; o->N = N; o->ldA = ldA; o->ldN = round_up(N, 4); o->A = A; o->has_target = (B != nullptr);
   // A few rows past a multiple of 128 (the Nyquist bin of a 513-bin spectrum) would cost a whole 128-row MMA
   // tile; they are handled as dot products on the CUDA cores instead.
@@ -991,6 +1069,21 @@ inline int build_operands(DictOperands* o, int mode, const float* A, const float
     simt::transpose_kernel<<<tg, tb, 0, s>>>(B, ldA, o->BT, o->ldN, N, F);
     EVC_LAUNCH_CHECK();
     EVC_TRY(make_tmap(&o->tmBT, o->BT, o->F_main, N, o->ldN, bk, 128));
+  }
+  if (mode == EVC_MODE_BF16) {
+    const int bk16 = bk_elems(mode);
+    o->ldA16 = round_up(F, 8); o->ldN16 = round_up(N, 8);
+    EVC_CUDA(cudaMalloc(&o->A16, (size_t)N * o->ldA16 * sizeof(__nv_bfloat16)));
+    EVC_CUDA(cudaMalloc(&o->AT16, (size_t)F * o->ldN16 * sizeof(__nv_bfloat16)));
+    EVC_TRY(launch_to_bf16(A, ldA, o->A16, o->ldA16, N, F, s));
+    EVC_TRY(launch_to_bf16(o->AT, o->ldN, o->AT16, o->ldN16, F, N, s));
+    EVC_TRY(make_tmap16(&o->tmA16, o->A16, N, F, o->ldA16, bk16, 128));
+    EVC_TRY(make_tmap16(&o->tmAT16, o->AT16, o->F_main, N, o->ldN16, bk16, 128));
+    if (B) {
+      EVC_CUDA(cudaMalloc(&o->BT16, (size_t)F * o->ldN16 * sizeof(__nv_bfloat16)));
+      EVC_TRY(launch_to_bf16(o->BT, o->ldN, o->BT16, o->ldN16, F, N, s));
+      EVC_TRY(make_tmap16(&o->tmBT16, o->BT16, o->F_main, N, o->ldN16, bk16, 128));
+    }
   }
   return EVC_OK;
 }
@@ -1046,11 +1139,17 @@ inline int left_ld(int T) { return round_up(T, kC2BlockT); }
 
 inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, int T, DevBuf* ws, cudaStream_t s) {
   if (mode == EVC_MODE_FP32) return EVC_OK;
-  const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
-  const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
+  const C1Plan pl = plan_c1(o.F_main, o.N, T, bk_elems(mode));
   o.left_valid = false;
   const size_t left = (size_t)left_rows(o) * o.n_left * left_ld(T);
-  return ws->reserve((ws_left_offset(pl, T) + left) * sizeof(float));
+  EVC_TRY(ws->reserve((ws_left_offset(pl, T) + left) * sizeof(float)));
+  if (mode == EVC_MODE_BF16) {
+    // the bf16 shadow of these activations (afterwards the fused update keeps it current) and room for the ratio
+    EVC_TRY(o.h16.reserve((size_t)T * o.ldN16 * sizeof(__nv_bfloat16)));
+    EVC_TRY(o.r16.reserve((size_t)T * o.ldA16 * sizeof(__nv_bfloat16)));
+    EVC_TRY(launch_to_bf16(H, ldH, o.h16.as<__nv_bfloat16>(), o.ldN16, T, o.N, s));
+  }
+  return EVC_OK;
 }
 
 struct RatioArgs {  // fuse R = X / max(WH, eps) into the split-K reduction
@@ -1058,23 +1157,26 @@ struct RatioArgs {  // fuse R = X / max(WH, eps) into the split-K reduction
 };
 
 inline int launch_ratio(const float* X, int ldX, const float* WH, int ldWH, float* R, int ldR, int T, int F,
-                        float eps, int copy, cudaStream_t s) {
+                        float eps, int copy, cudaStream_t s, __nv_bfloat16* R16 = nullptr, int ldR16 = 0) {
   ProfScope ps(1, s);
-  dim3 g(T, ceil_div(ldR, 128));
-  ratio_pad_kernel<<<g, 128, 0, s>>>(X, ldX, WH, ldWH, R, ldR, T, F, eps, copy);
+  dim3 g(T, ceil_div(R16 ? ldR16 : ldR, 128));
+  ratio_pad_kernel<<<g, 128, 0, s>>>(X, ldX, WH, ldWH, R, ldR, T, F, eps, copy, R16, ldR16);
   EVC_LAUNCH_CHECK();
   return EVC_OK;
 }
 
-template <bool kSplit3, int kCG>
+template <bool kSplit3, int kCG, bool kBf16 = false>
 inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
                          DevBuf* ws, cudaStream_t s, const RatioArgs* ra) {
-  constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;
-  const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
+  constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;   // K-block in 4-byte words (the kernel's template argument)
+  constexpr int bke = kBf16 ? 2 * bk : bk;            // ... in elements
+  const C1Plan pl = plan_c1(o.F_main, o.N, T, bke);
   float* partials = ws->as<float>();
   float* leftp = ws->as<float>() + ws_left_offset(pl, T);
   CUtensorMap tmH;
-  EVC_TRY(make_tmap(&tmH, H, T, o.N, ldH, bk, kC1BlockT / kCG));
+  // BF16: the K operand is the shadow of H (made by after_h_written, kept current by the fused update)
+  if (kBf16) EVC_TRY(make_tmap16(&tmH, o.h16.as<__nv_bfloat16>(), T, o.N, o.ldN16, bke, kC1BlockT / kCG));
+  else EVC_TRY(make_tmap(&tmH, H, T, o.N, ldH, bk, kC1BlockT / kCG));
   GemmParams p{};
   p.M_total = o.F_main; p.T = T; p.K = o.N;
   p.num_m_groups = pl.m_groups; p.num_t_tiles = pl.t_tiles; p.num_splits = pl.splits;
@@ -1085,7 +1187,8 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
   p.out = partials; p.ld_out = pl.ldp;
   {
     ProfScope ps(0, s);
-    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL, kCG>(target ? o.tmBT : o.tmAT, tmH, tmH, tmH, p, s)));
+    const CUtensorMap& tmD = kBf16 ? (target ? o.tmBT16 : o.tmAT16) : (target ? o.tmBT : o.tmAT);
+    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, bk, kSplit3, TEPI_PARTIAL, kCG, kBf16>(tmD, tmH, tmH, tmH, p, s)));
   }
   // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
   const bool from_partials = o.n_left > 0 && !target && o.left_valid;
@@ -1103,7 +1206,8 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
     EVC_CUDA(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, (const float*)partials, pl.splits, pl.splits_last, pl.f_last, T,
                                 pl.ldp, o.F, o.F_main, WH, ldWH, (const float*)leftp, from_partials ? left_rows(o) : 0,
                                 o.n_left, left_ld(T), fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0,
-                                fuse ? ra->R : (float*)nullptr, fuse ? ra->ldR : 0, fuse ? ra->eps : 0.f));
+                                (fuse && !kBf16) ? ra->R : (float*)nullptr, fuse ? ra->ldR : 0, fuse ? ra->eps : 0.f,
+                                (fuse && kBf16) ? o.r16.as<__nv_bfloat16>() : (__nv_bfloat16*)nullptr, o.ldA16));
     EVC_LAUNCH_CHECK();
     if (standalone) {
       const float* rows = (target ? o.BT : o.AT) + (size_t)o.F_main * o.ldN;
@@ -1111,7 +1215,9 @@ inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float*
       EVC_LAUNCH_CHECK();
     }
   }
-  if (ra && standalone) EVC_TRY(launch_ratio(ra->X, ra->ldX, WH, ldWH, ra->R, ra->ldR, T, o.F, ra->eps, 0, s));
+  if (ra && standalone)
+    EVC_TRY(launch_ratio(ra->X, ra->ldX, WH, ldWH, ra->R, ra->ldR, T, o.F, ra->eps, 0, s,
+                         kBf16 ? o.r16.as<__nv_bfloat16>() : nullptr, o.ldA16));
   return EVC_OK;
 }
 
@@ -1120,21 +1226,25 @@ inline int contract_wh(DictOperands& o, int mode, const float* H, int ldH, int T
   if (target && !o.has_target) return fail(EVC_ERR_INVALID_ARGUMENT, "no target dictionary");
   if (cta_group() == 2) {
     if (mode == EVC_MODE_3XTF32) return contract_wh_t<true, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+    if (mode == EVC_MODE_BF16) return contract_wh_t<false, 2, true>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
     return contract_wh_t<false, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
   }
   if (mode == EVC_MODE_3XTF32) return contract_wh_t<true, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  if (mode == EVC_MODE_BF16) return contract_wh_t<false, 1, true>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
   return contract_wh_t<false, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
 }
 
 // Second contraction with a fused epilogue.  `R` is what multiplies A^T: the ratio (KL) or A H (Frobenius).
-template <bool kSplit3, int kEpi, int kCG>
+template <bool kSplit3, int kEpi, int kCG, bool kBf16>
 inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmParams p, cudaStream_t s) {
   constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;
+  constexpr int bke = kBf16 ? 2 * bk : bk;
   CUtensorMap tmR;
-  EVC_TRY(make_tmap(&tmR, R, T, o.F, ldR, bk, kC2BlockT / kCG));
+  if (kBf16) EVC_TRY(make_tmap16(&tmR, o.r16.as<__nv_bfloat16>(), T, o.F, o.ldA16, bke, kC2BlockT / kCG));
+  else EVC_TRY(make_tmap(&tmR, R, T, o.F, ldR, bk, kC2BlockT / kCG));
   p.M_total = o.N; p.T = T; p.K = o.F;
   p.num_m_groups = ceil_div(o.N, 128 * kC2MTiles * kCG); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
-  p.kblocks_total = ceil_div(o.F, bk); p.kblocks_per_split = p.kblocks_total;
+  p.kblocks_total = ceil_div(o.F, bke); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
   {
     // tail balancing: the tiles of a last, less-than-half-filled round run as two half-width items each
@@ -1146,63 +1256,68 @@ inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmPar
   p.m_fastest = getenv("EVC_T_FASTEST") ? 0 : 1;
   p.direct_store = getenv("EVC_DIRECT_STORE") ? 1 : 0;
   CUtensorMap tmHc = tmR, tmQc = tmR;  // the fused updates stage H (and the Frobenius numerator) through shared memory
+  if (kBf16 && (kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO)) { p.out16 = o.h16.as<__nv_bfloat16>(); p.ld_out16 = o.ldN16; }
   if (kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
   if (kEpi == TEPI_MU_FRO) EVC_TRY(make_tmap(&tmQc, p.num0, T, o.N, p.ld_out, 128, kHChunkT, false));
   ProfScope ps(2, s);
-  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi, kCG>(o.tmA, tmR, tmHc, tmQc, p, s);
+  return launch_tc<kC2MTiles, kC2BlockT, bk, kSplit3, kEpi, kCG, kBf16>(kBf16 ? o.tmA16 : o.tmA, tmR, tmHc, tmQc, p, s);
 }
 
-template <bool kSplit3, int kEpi>
-inline int contract2_t(DictOperands& o, int T, const float* R, int ldR, const GemmParams& p, cudaStream_t s) {
-  if (cta_group() == 2) return contract2_cg<kSplit3, kEpi, 2>(o, T, R, ldR, p, s);
-  return contract2_cg<kSplit3, kEpi, 1>(o, T, R, ldR, p, s);
+template <int kEpi>
+inline int contract2_t(DictOperands& o, int mode, int T, const float* R, int ldR, const GemmParams& p, cudaStream_t s) {
+  if (cta_group() == 2) {
+    if (mode == EVC_MODE_3XTF32) return contract2_cg<true, kEpi, 2, false>(o, T, R, ldR, p, s);
+    if (mode == EVC_MODE_BF16) return contract2_cg<false, kEpi, 2, true>(o, T, R, ldR, p, s);
+    return contract2_cg<false, kEpi, 2, false>(o, T, R, ldR, p, s);
+  }
+  if (mode == EVC_MODE_3XTF32) return contract2_cg<true, kEpi, 1, false>(o, T, R, ldR, p, s);
+  if (mode == EVC_MODE_BF16) return contract2_cg<false, kEpi, 1, true>(o, T, R, ldR, p, s);
+  return contract2_cg<false, kEpi, 1, false>(o, T, R, ldR, p, s);
 }
 
 inline int update_kl(DictOperands& o, int mode, const float* X, int ldX, int T, const float* WH, int ldWH, float* R,
                      int ldR, float* H, int ldH, const float* colsum, float lam, float eps,
                      const unsigned char* row_active, DevBuf* ws, cudaStream_t s, bool ratio_done = false) {
-  if (!ratio_done) EVC_TRY(launch_ratio(X, ldX, WH, ldWH, R, ldR, T, o.F, eps, 0, s));
+  __nv_bfloat16* R16 = (mode == EVC_MODE_BF16) ? o.r16.as<__nv_bfloat16>() : nullptr;
+  if (!ratio_done) EVC_TRY(launch_ratio(X, ldX, WH, ldWH, R, ldR, T, o.F, eps, 0, s, R16, o.ldA16));
   GemmParams p{};
   p.out = H; p.ld_out = ldH;
   p.colsum = colsum; p.lam = lam; p.eps = eps; p.row_active = row_active;
   if (o.n_left > 0) {
-    const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
-    const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
+    const C1Plan pl = plan_c1(o.F_main, o.N, T, bk_elems(mode));
     p.left_a = o.AT + (size_t)o.F_main * o.ldN; p.left_lda = o.ldN; p.n_left = o.n_left;
     p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T); p.left_rows = left_rows(o);
     o.left_valid = true;  // (stream order: the partials are complete before the next contraction 1 reads them)
   }
-  if (mode == EVC_MODE_3XTF32) return contract2_t<true, TEPI_MU_KL>(o, T, R, ldR, p, s);
-  return contract2_t<false, TEPI_MU_KL>(o, T, R, ldR, p, s);
+  return contract2_t<TEPI_MU_KL>(o, mode, T, R, ldR, p, s);
 }
 
 inline int update_fro(DictOperands& o, int mode, int T, const float* WH, int ldWH, float* R, int ldR, float* H, int ldH,
                       const float* num0, float lam, float eps, const unsigned char* row_active, DevBuf* ws,
                       cudaStream_t s) {
-  EVC_TRY(launch_ratio(nullptr, 0, WH, ldWH, R, ldR, T, o.F, eps, 1, s));
+  EVC_TRY(launch_ratio(nullptr, 0, WH, ldWH, R, ldR, T, o.F, eps, 1, s,
+                       (mode == EVC_MODE_BF16) ? o.r16.as<__nv_bfloat16>() : nullptr, o.ldA16));
   GemmParams p{};
   p.out = H; p.ld_out = ldH;
   p.num0 = num0; p.lam = lam; p.eps = eps; p.row_active = row_active;
   if (o.n_left > 0) {
-    const int bk = (mode == EVC_MODE_3XTF32) ? kBlockK3 : kBlockK1;
-    const C1Plan pl = plan_c1(o.F_main, o.N, T, bk);
+    const C1Plan pl = plan_c1(o.F_main, o.N, T, bk_elems(mode));
     p.left_a = o.AT + (size_t)o.F_main * o.ldN; p.left_lda = o.ldN; p.n_left = o.n_left;
     p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T); p.left_rows = left_rows(o);
     o.left_valid = true;
   }
-  if (mode == EVC_MODE_3XTF32) return contract2_t<true, TEPI_MU_FRO>(o, T, R, ldR, p, s);
-  return contract2_t<false, TEPI_MU_FRO>(o, T, R, ldR, p, s);
+  return contract2_t<TEPI_MU_FRO>(o, mode, T, R, ldR, p, s);
 }
 
 // NUM0 (T, ldH) = X A^T : the second contraction with a plain store ([split=0][t][n] layout == (T, ldH)).
 inline int frob_numerator(DictOperands& o, int mode, const float* X, int ldX, int T, float* R, int ldR, float* num0,
                           int ldH, DevBuf* ws, cudaStream_t s) {
   // stage X into the zero-padded K-operand buffer (copy mode of the ratio kernel with WH := X)
-  EVC_TRY(launch_ratio(nullptr, 0, X, ldX, R, ldR, T, o.F, 0.f, 1, s));
+  EVC_TRY(launch_ratio(nullptr, 0, X, ldX, R, ldR, T, o.F, 0.f, 1, s,
+                       (mode == EVC_MODE_BF16) ? o.r16.as<__nv_bfloat16>() : nullptr, o.ldA16));
   GemmParams p{};
   p.out = num0; p.ld_out = ldH;
-  if (mode == EVC_MODE_3XTF32) return contract2_t<true, TEPI_PARTIAL>(o, T, R, ldR, p, s);
-  return contract2_t<false, TEPI_PARTIAL>(o, T, R, ldR, p, s);
+  return contract2_t<TEPI_PARTIAL>(o, mode, T, R, ldR, p, s);
 }
 
 }  // namespace tc

@@ -197,6 +197,25 @@ __device__ __forceinline__ void mma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one MMA of the selected kind / CTA group (kBf16: kind::f16 with bf16 operands, else kind::tf32)
+template <bool kBf16, int kCG>
+__device__ __forceinline__ void mma_issue(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (kBf16) {
+    if (kCG == 2) mma_f16_2cta(tmem_d, adesc, bdesc, idesc, accumulate);
+    else mma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    if (kCG == 2) mma_tf32_2cta(tmem_d, adesc, bdesc, idesc, accumulate);
+    else mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
 // arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair when the MMAs retire
 __device__ __forceinline__ void mma_commit_2cta(uint32_t bar) {
   const uint16_t mask = 3;
