@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libevc_b200.so")
+# EVC_LIB_PATH: load another build of the same library (A/B runs of compile-time variants); still no fallback.
+LIB_PATH = os.environ.get("EVC_LIB_PATH") or os.path.join(HERE, "libevc_b200.so")
 
 EVC_OK, EVC_ERR_INVALID_ARGUMENT, EVC_ERR_CUDA, EVC_ERR_UNSUPPORTED, EVC_ERR_VALUE, EVC_ERR_COMM = range(6)
 MODE_FP32, MODE_3XTF32, MODE_TF32, MODE_BF16 = range(4)

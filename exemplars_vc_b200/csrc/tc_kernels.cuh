@@ -17,6 +17,13 @@
 // D += M_lo*N_hi + M_hi*N_lo + M_hi*N_hi, dropping lo*lo (2^-22 relative).  HBM and L2 only ever carry one
 // fp32 copy of each operand.
 //
+// kSplit3 == 2 ("cross16") keeps hi*hi on kind::tf32 and runs the two small cross terms on kind::f16 with bf16
+// operands, M_lo16*N_hi16 + M_hi16*N_lo16 (hi16 = bf16(x), lo16 = bf16(x - trunc_tf32(x))): a bf16 MMA covers
+// 16 K elements in the time a tf32 MMA covers 8, so a product costs 2 MMA passes instead of 3 and a third less
+// operand traffic out of shared memory, for a per-term error of ~2^-20 (lo is <= 2^-10 |x| and is itself kept to
+// 2^-9) on top of the dropped lo*lo.  The split warps write the two bf16 tiles (32-byte rows, 32B swizzle) where
+// the fp32 lo tile used to be.
+//
 // BF16 fast mode (kBf16): the same kernel with tcgen05.mma.kind::f16 on bf16 operand copies -- the dictionary is
 // converted once, the ratio is emitted in bf16 by the reduction pass, and the fused update writes a bf16 shadow of
 // the activations next to the fp32 master copy (the multiplicative update itself stays fp32).  A K-block is still
@@ -132,7 +139,10 @@ __device__ __forceinline__ float tf32_lo(float x) {
 
 constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, interleaved over 32-column chunks
 constexpr int kXformWarps = 8;  // dedicated hi/lo split warps (only when the epilogue overlaps the main loop)
-constexpr int kWarpsPerStage = 2;  // split warps that share one ring stage (groups take K-blocks round-robin)
+#ifndef EVC_WARPS_PER_STAGE
+#define EVC_WARPS_PER_STAGE 2
+#endif
+constexpr int kWarpsPerStage = EVC_WARPS_PER_STAGE;  // split warps that share one ring stage (groups take K-blocks round-robin)
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 // The fused-update epilogue stages H through shared memory in [32 frames x 128 exemplars] chunks moved by TMA
@@ -144,7 +154,7 @@ constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = 4;
 // tcgen05.mma.cta_group::2 with M = 256 (128 dictionary rows per CTA) and the frame (N) operand split in halves
 // between the two CTAs' shared memories, which halves the per-SM shared-memory reads of the frame operand
 // (the 3xTF32 main loop of the 1-CTA version is shared-memory-bandwidth bound).
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, bool kStageH, int kCG, bool kStageQ = false>
+template <int kMTiles, int kBlockT, int kBlockK, int kSplit3, bool kStageH, int kCG, bool kStageQ = false>
 struct TileCfg {
   static constexpr int kRowBytes = kBlockK * 4;
   static constexpr int kMTileBytes = 128 * kRowBytes;              // this CTA's 128 rows of one dictionary sub-tile
@@ -188,6 +198,7 @@ struct TileCfg {
   static_assert(kBlockT % 32 == 0 && kBlockT >= 32 && kBlockT <= 256, "bad frame tile");
   static_assert(!kStageH || kMTiles == 1, "H staging assumes one sub-tile per work item");
   static_assert(kCG == 1 || kCG == 2, "CTA group is 1 or 2");
+  static_assert(kSplit3 != 2 || kRowBytes == 64, "the bf16 cross-term tiles are derived from 64-byte rows");
 };
 
 // lo = x - trunc_tf32(x) for one ring stage: element-wise on raw bytes, so the swizzled layout TMA wrote
@@ -211,15 +222,62 @@ __device__ __forceinline__ void split_region(const uint8_t* hi, uint8_t* lo, int
       dst[(q0 + q) * 32] = make_float4(tf32_lo(x[q].x), tf32_lo(x[q].y), tf32_lo(x[q].z), tf32_lo(x[q].w));
   }
 }
+// cross16: from one fp32 tile (64-byte rows, 64B swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3))
+// derive hi16 = bf16(x) and lo16 = bf16(x - trunc_tf32(x)) as tiles with 32-byte rows in the 32B-swizzle layout
+// (chunk c of row r at chunk c ^ ((r >> 2) & 1)).  A unit is half a row: 8 floats in, 16 + 16 bytes out.
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <int kRows>
+__device__ __forceinline__ void split16_tile(const uint8_t* src, uint8_t* hi16, uint8_t* lo16, int lane, int part) {
+  constexpr int kShare = kRows * 2 / kWarpsPerStage, kPerLane = kShare / 32;
+  constexpr int kBatch = kPerLane < 4 ? kPerLane : 4;  // units in flight per lane
+  static_assert(kPerLane >= 1 && kPerLane % kBatch == 0, "tile too small for the split warps");
+#pragma unroll
+  for (int b = 0; b < kPerLane; b += kBatch) {
+    float4 x[kBatch][2];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const int u = part * kShare + (b + q) * 32 + lane, row = u >> 1, h = u & 1, sw = (row >> 1) & 3;
+      const uint8_t* r = src + row * 64;
+      x[q][0] = *reinterpret_cast<const float4*>(r + (((2 * h) ^ sw) << 4));
+      x[q][1] = *reinterpret_cast<const float4*>(r + (((2 * h + 1) ^ sw) << 4));
+    }
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const int u = part * kShare + (b + q) * 32 + lane, row = u >> 1, h = u & 1;
+      const int off = row * 32 + ((h ^ ((row >> 2) & 1)) << 4);
+      const float4 a = x[q][0], c = x[q][1];
+      *reinterpret_cast<uint4*>(hi16 + off) =
+          make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+      *reinterpret_cast<uint4*>(lo16 + off) =
+          make_uint4(pack_bf16(tf32_lo(a.x), tf32_lo(a.y)), pack_bf16(tf32_lo(a.z), tf32_lo(a.w)),
+                     pack_bf16(tf32_lo(c.x), tf32_lo(c.y)), pack_bf16(tf32_lo(c.z), tf32_lo(c.w)));
+    }
+  }
+}
+template <class Cfg, int kMTiles>
+__device__ __forceinline__ void split16_stage(uint8_t* stage, int lane, int part) {
+  // derived region of dictionary sub-tile i: [hi16 | lo16] where the fp32 lo tile of the classic split would be
+#pragma unroll
+  for (int i = 0; i < kMTiles; ++i) {
+    uint8_t* d = stage + Cfg::kOffMlo + i * Cfg::kMTileBytes;
+    split16_tile<128>(stage + i * Cfg::kMTileBytes, d, d + Cfg::kMTileBytes / 2, lane, part);
+  }
+  uint8_t* d = stage + Cfg::kOffNlo;
+  split16_tile<Cfg::kNRows>(stage + Cfg::kOffN, d, d + Cfg::kNTileBytes / 2, lane, part);
+}
+
 template <class Cfg>
 __device__ __forceinline__ void split_stage(uint8_t* stage, int lane, int part) {
-  static_assert(Cfg::kMBytes % (4096 * kWarpsPerStage) == 0 && Cfg::kNTileBytes % (4096 * kWarpsPerStage) == 0,
+  static_assert(Cfg::kMBytes % (2048 * kWarpsPerStage) == 0 && Cfg::kNTileBytes % (2048 * kWarpsPerStage) == 0,
                 "every split warp must get a multiple of 2 KB per region");
   split_region<Cfg>(stage, stage + Cfg::kOffMlo, Cfg::kMBytes, lane, part);
   split_region<Cfg>(stage + Cfg::kOffN, stage + Cfg::kOffNlo, Cfg::kNTileBytes, lane, part);
 }
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG, bool kBf16 = false>
+template <int kMTiles, int kBlockT, int kBlockK, int kSplit3, int kEpi, int kCG, bool kBf16 = false>
 __global__ void __launch_bounds__(
     (TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO, kCG, kEpi == TEPI_MU_FRO>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
@@ -235,6 +293,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   constexpr int kKE = kBf16 ? 2 * kBlockK : kBlockK;  // K elements per K-block (one swizzle row)
   constexpr int kKStep = kBf16 ? 16 : 8;              // K elements per MMA (32 bytes either way)
   constexpr uint32_t kIdesc = make_idesc(kFmt, 128 * kCG, kBlockT);
+  constexpr bool kCross16 = (kSplit3 == 2);
   // does the MMA warp wait on the "ready" barrier (split and/or pair) or directly on the TMA barrier?
   constexpr bool kUseReady = kSplit3 || kCG == 2;
 
@@ -386,6 +445,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles);
         const int kb0 = w.kb0, kb1 = w.kb1;
         const uint32_t idesc = (w.t_cols == kBlockT) ? kIdesc : make_idesc(kFmt, 128 * kCG, (uint32_t)w.t_cols);
+        const uint32_t idesc16 = make_idesc(kFmtBF16, 128 * kCG, (uint32_t)w.t_cols);  // cross16: the bf16 cross terms
         long long c0 = clock64();
         if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
         else mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
@@ -407,6 +467,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             if (m0 + i * Cfg::kRowsPerSub >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
             if (p.debug_flags & 2) break;
             const uint32_t d = tmem_base + (uint32_t)((acc * kMTiles + i) * kBlockT);
+            if (kCross16) {
+              // small terms first: lo16*hi16 + hi16*lo16 over the whole K-block (one 16-element bf16 MMA each;
+              // a K tail was zero-filled by TMA), then hi*hi in tf32
+              const uint32_t a16 = sbase + Cfg::kOffMlo + i * Cfg::kMTileBytes, b16 = nbase + Cfg::kNTileBytes;
+              const uint64_t a_hi16 = make_smem_desc(a16, 32), a_lo16 = make_smem_desc(a16 + Cfg::kMTileBytes / 2, 32);
+              const uint64_t b_hi16 = make_smem_desc(b16, 32), b_lo16 = make_smem_desc(b16 + Cfg::kNTileBytes / 2, 32);
+              mma_issue<true, kCG>(d, a_lo16, b_hi16, idesc16, kb > kb0 ? 1u : 0u);
+              mma_issue<true, kCG>(d, a_hi16, b_lo16, idesc16, 1u);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t a_hi = make_smem_desc(sbase + i * Cfg::kMTileBytes + ks * 32, Cfg::kRowBytes);
+                const uint64_t b_hi = make_smem_desc(nbase + ks * 32, Cfg::kRowBytes);
+                mma_issue<false, kCG>(d, a_hi, b_hi, idesc, 1u);
+              }
+            } else
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
               const uint64_t a_hi = make_smem_desc(sbase + i * Cfg::kMTileBytes + ks * 32, Cfg::kRowBytes);
@@ -514,7 +588,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           if (seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
             const long long t1 = clock64();
             if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
-            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
+            if (!(p.debug_flags & 1)) {
+              if (kCross16) split16_stage<Cfg, kMTiles>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
+              else split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
+            }
             fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
             __syncwarp();
             if (lane == 0) ready_arrive(stage);
@@ -552,7 +629,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           if (split_seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
             const long long t1 = clock64();
             if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
-            if (!(p.debug_flags & 1)) split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
+            if (!(p.debug_flags & 1)) {
+              if (kCross16) split16_stage<Cfg, kMTiles>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
+              else split_stage<Cfg>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ready_arrive(stage);
@@ -941,7 +1021,7 @@ inline bool use_pdl() {
   return on;
 }
 
-template <int kMTiles, int kBlockT, int kBlockK, bool kSplit3, int kEpi, int kCG, bool kBf16 = false>
+template <int kMTiles, int kBlockT, int kBlockK, int kSplit3, int kEpi, int kCG, bool kBf16 = false>
 inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const CUtensorMap& tmQ,
                      const GemmParams& p, cudaStream_t s) {
   using Cfg = TileCfg<kMTiles, kBlockT, kBlockK, kSplit3, kEpi == TEPI_MU_KL || kEpi == TEPI_MU_FRO, kCG, kEpi == TEPI_MU_FRO>;
@@ -1011,6 +1091,12 @@ inline int bk_elems(int mode) {
 }
 
 // CTA group of the MMAs: 2 (CTA pairs, default) or 1 (EVC_CTA_GROUP=1: single-CTA kernels, kept for A/B runs).
+// fp32-accurate mode: 2 = tf32 hi*hi + two bf16 cross-term MMAs (default), 1 = three tf32 MMAs per product
+// (EVC_SPLIT_CROSS16=0; kept for A/B runs and as the accuracy reference)
+inline int split_flavor() {
+  static const int f = (getenv("EVC_SPLIT_CROSS16") && atoi(getenv("EVC_SPLIT_CROSS16")) == 0) ? 1 : 2;
+  return f;
+}
 inline int cta_group() {
   static const int cg = (getenv("EVC_CTA_GROUP") && atoi(getenv("EVC_CTA_GROUP")) == 1) ? 1 : 2;
   return cg;
@@ -1165,7 +1251,7 @@ inline int launch_ratio(const float* X, int ldX, const float* WH, int ldWH, floa
   return EVC_OK;
 }
 
-template <bool kSplit3, int kCG, bool kBf16 = false>
+template <int kSplit3, int kCG, bool kBf16 = false>
 inline int contract_wh_t(DictOperands& o, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
                          DevBuf* ws, cudaStream_t s, const RatioArgs* ra) {
   constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;   // K-block in 4-byte words (the kernel's template argument)
@@ -1225,17 +1311,19 @@ inline int contract_wh(DictOperands& o, int mode, const float* H, int ldH, int T
                        DevBuf* ws, cudaStream_t s, const RatioArgs* ra = nullptr) {
   if (target && !o.has_target) return fail(EVC_ERR_INVALID_ARGUMENT, "no target dictionary");
   if (cta_group() == 2) {
-    if (mode == EVC_MODE_3XTF32) return contract_wh_t<true, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+    if (mode == EVC_MODE_3XTF32 && split_flavor() == 2) return contract_wh_t<2, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+    if (mode == EVC_MODE_3XTF32) return contract_wh_t<1, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
     if (mode == EVC_MODE_BF16) return contract_wh_t<false, 2, true>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
     return contract_wh_t<false, 2>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
   }
-  if (mode == EVC_MODE_3XTF32) return contract_wh_t<true, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  if (mode == EVC_MODE_3XTF32 && split_flavor() == 2) return contract_wh_t<2, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  if (mode == EVC_MODE_3XTF32) return contract_wh_t<1, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
   if (mode == EVC_MODE_BF16) return contract_wh_t<false, 1, true>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
   return contract_wh_t<false, 1>(o, H, ldH, T, WH, ldWH, target, ws, s, ra);
 }
 
 // Second contraction with a fused epilogue.  `R` is what multiplies A^T: the ratio (KL) or A H (Frobenius).
-template <bool kSplit3, int kEpi, int kCG, bool kBf16>
+template <int kSplit3, int kEpi, int kCG, bool kBf16>
 inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmParams p, cudaStream_t s) {
   constexpr int bk = kSplit3 ? kBlockK3 : kBlockK1;
   constexpr int bke = kBf16 ? 2 * bk : bk;
@@ -1266,11 +1354,13 @@ inline int contract2_cg(DictOperands& o, int T, const float* R, int ldR, GemmPar
 template <int kEpi>
 inline int contract2_t(DictOperands& o, int mode, int T, const float* R, int ldR, const GemmParams& p, cudaStream_t s) {
   if (cta_group() == 2) {
-    if (mode == EVC_MODE_3XTF32) return contract2_cg<true, kEpi, 2, false>(o, T, R, ldR, p, s);
+    if (mode == EVC_MODE_3XTF32 && split_flavor() == 2) return contract2_cg<2, kEpi, 2, false>(o, T, R, ldR, p, s);
+    if (mode == EVC_MODE_3XTF32) return contract2_cg<1, kEpi, 2, false>(o, T, R, ldR, p, s);
     if (mode == EVC_MODE_BF16) return contract2_cg<false, kEpi, 2, true>(o, T, R, ldR, p, s);
     return contract2_cg<false, kEpi, 2, false>(o, T, R, ldR, p, s);
   }
-  if (mode == EVC_MODE_3XTF32) return contract2_cg<true, kEpi, 1, false>(o, T, R, ldR, p, s);
+  if (mode == EVC_MODE_3XTF32 && split_flavor() == 2) return contract2_cg<2, kEpi, 1, false>(o, T, R, ldR, p, s);
+  if (mode == EVC_MODE_3XTF32) return contract2_cg<1, kEpi, 1, false>(o, T, R, ldR, p, s);
   if (mode == EVC_MODE_BF16) return contract2_cg<false, kEpi, 1, true>(o, T, R, ldR, p, s);
   return contract2_cg<false, kEpi, 1, false>(o, T, R, ldR, p, s);
 }
