@@ -270,8 +270,32 @@ def main():
     value = frames_total / (ms_step * 1e-3)
     e2e_value = frames_total / (e2e_step * 1e-3)
 
+    def measured_matmul_tflops(dtype):
+        """Dense library GEMM rate in this run (MEASURED_PEAKS.json has no TF32 figure): torch.matmul
+        8192^3, a cross-check of the 1/2 x bf16 denominator, not the denominator itself."""
+        n = 8192
+        a = torch.randn(n, n, device=dev, dtype=dtype); b = torch.randn(n, n, device=dev, dtype=dtype)
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            for _ in range(3):
+                a @ b
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(10):
+                a @ b
+            t1.record(); torch.cuda.synchronize()
+            return 10 * 2.0 * n ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old
+
     if rank == 0:
         peaks = load_peaks()
+        try:
+            lib_gemm = {"tf32_matmul_tflops": round(measured_matmul_tflops(torch.float32), 1),
+                        "bf16_matmul_tflops": round(measured_matmul_tflops(torch.bfloat16), 1)}
+        except Exception as e:      # diagnostics only
+            lib_gemm = {"error": str(e)[:100]}
         n_local = (wl.N if not exemplar_sharded else (n1 - n0))
         # dominant kernel: contraction 2 (R A^T with the fused multiplicative update); algorithmic work per
         # launch = 2*T*F*N_local flop (SURVEY 8d: 4*F*N per frame per iteration, half in each contraction)
@@ -280,7 +304,7 @@ def main():
         per_launch_s = (c2_ms / max(c2_n, 1)) * 1e-3
         flop = 2.0 * wl.T * wl.F * n_local
         achieved = flop / per_launch_s / 1e12 if per_launch_s > 0 else 0.0
-        passes = 3 if args.mode == "3xtf32" else 1
+        passes = max(1, int(_lib.lib().evc_mma_passes_per_product(_lib.MODES[args.mode])))
         tf32_peak = peaks["bf16_tflops_sustained"] / (1.0 if args.mode == "bf16" else 2.0)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -295,7 +319,7 @@ def main():
                     "peak_source": ("dense BF16 = bf16_tflops_sustained, " if args.mode == "bf16" else
                                     "dense TF32 = 1/2 of bf16_tflops_sustained, ") + peaks["_source"],
                     "executed_tflops": achieved * passes, "executed_frac": achieved * passes / tf32_peak,
-                    "mma_passes_per_product": passes,
+                    "mma_passes_per_product": passes, "library_gemm_this_run": lib_gemm,
                     "us_per_launch": per_launch_s * 1e6,
                     "step_share": {k: round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4) for k, v in prof.items()},
                     "contraction1_us_per_launch": c1_ms / max(c1_n, 1) * 1e3,

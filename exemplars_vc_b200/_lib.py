@@ -51,6 +51,8 @@ def lib():
     L.evc_last_error_string.restype = C.c_char_p
     L.evc_kernel_launch_count.restype = C.c_longlong
     L.evc_last_enqueue_ms.restype = C.c_double
+    L.evc_mma_passes_per_product.argtypes = [C.c_int]
+    L.evc_mma_passes_per_product.restype = C.c_int
     L.evc_default_params.argtypes = [C.POINTER(SolveParams)]
     L.evc_default_params.restype = None
     L.evc_dict_create.argtypes = [vp, ip, vp, ip, ip, ip, ip, vp, C.POINTER(vp)]

@@ -74,7 +74,8 @@ struct GemmParams {
   float* left_out;      // [l][t][row] partial sums, row = 4*(128-exemplar block) + lane quarter
   int left_ld, left_rows;  // frames pitch, rows pitch
   long long* dbg_cycles;  // EVC_DEBUG_TIMING: per-CTA [8] cycle counters of the role threads (nullptr = off)
-  int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops, 16 enable the L2 look-ahead prefetch
+  int debug_flags;  // timing experiments only (EVC_DEBUG_FLAGS): 1 skip split, 2 skip MMA, 4 skip TMA, 8 skip epilogue memory ops, 16 enable the L2 look-ahead prefetch,
+                    // 32 / 64 skip the frame-side / dictionary-side operand loads, 128 skip the H chunk loads and stores of the fused update
 };
 
 // vals[j] (j = 0..31) per lane -> returns, in lane L, the sum over all 32 lanes of vals[L]  (31 shuffles).
@@ -144,11 +145,21 @@ constexpr int kXformWarps = 8;  // dedicated hi/lo split warps (only when the ep
 #endif
 constexpr int kWarpsPerStage = EVC_WARPS_PER_STAGE;  // split warps that share one ring stage (groups take K-blocks round-robin)
 constexpr int kSmemBudget = 227 * 1024 - 2048;
+// back-off (ns) between polls of the many-warp waits; 0 = spin
+#ifndef EVC_SPLIT_SLEEP_NS
+#define EVC_SPLIT_SLEEP_NS 0
+#endif
+#ifndef EVC_EPI_SLEEP_NS
+#define EVC_EPI_SLEEP_NS 0
+#endif
 
 // The fused-update epilogue stages H through shared memory in [32 frames x 128 exemplars] chunks moved by TMA
 // (loads prefetched by a loader warp, stores issued by a storer warp): per-lane 128-byte global accesses
 // from the epilogue warps were limited by the SM's outstanding-miss capacity, bulk copies are not.
-constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = 4;
+#ifndef EVC_H_BUFS
+#define EVC_H_BUFS 4
+#endif
+constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = EVC_H_BUFS;
 
 // kCG = CTA group size of the MMA.  1: one SM per tile.  2: a CTA pair (cluster of 2) shares each tile --
 // tcgen05.mma.cta_group::2 with M = 256 (128 dictionary rows per CTA) and the frame (N) operand split in halves
@@ -312,6 +323,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // cycle counter of the EVC_DEBUG_TIMING instrumentation: not read at all in normal runs (a CS2R per pipeline step
+  // of the single-thread roles is not free)
+  const bool dbg_on = p.dbg_cycles != nullptr;
+auto clk = [dbg_on]() -> long long { return dbg_on ? clock64() : 0ll; };
   const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   uint8_t* ring_ptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t ring = smem_u32(ring_ptr);
@@ -365,7 +380,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       long long c_empty = 0;
-      const long long c_start = clock64();
+      const long long c_start = clk();
       // L2 look-ahead: the tiles of K-block (current + kAhead) are prefetched into L2 when the current one is
       // loaded, so the ring refill sees L2 latency instead of HBM latency (the ring itself is only 3-6 deep).
       constexpr int kAhead = 2 * kStages;
@@ -407,30 +422,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             }
           }
           ++issued;
-          const long long c0 = clock64();
+          const long long c0 = clk();
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          c_empty += clock64() - c0;
+          c_empty += clk() - c0;
           const uint32_t full = smem_u32(&bar_full[stage]);
           if (p.debug_flags & 4) {
             mbar_arrive(full);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
             continue;
           }
-          mbar_arrive_expect_tx(full, (uint32_t)Cfg::kLoadBytes);
-          if (p.dbg_cycles) dbg_t_issue[stage] = clock64();
+          const bool skip_m = (p.debug_flags & 64) != 0, skip_n = (p.debug_flags & 32) != 0;  // timing experiments
+          mbar_arrive_expect_tx(full, (uint32_t)((skip_m ? 0 : Cfg::kMBytes) + (skip_n ? 0 : Cfg::kNTileBytes)));
+          if (p.dbg_cycles) dbg_t_issue[stage] = clk();
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
           const int kc = kb * kKE;
           // (sub-tiles past M_total are still loaded: TMA zero-fills them and the byte count stays constant)
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i)
-            tma_load_2d(sbase + i * Cfg::kMTileBytes, &tmM, kc, m0 + i * Cfg::kRowsPerSub, full, kEvictNormal);
-          tma_load_2d(sbase + Cfg::kOffN, &tmN, kc, t0, full, kEvictNormal);
+            if (!skip_m) tma_load_2d(sbase + i * Cfg::kMTileBytes, &tmM, kc, m0 + i * Cfg::kRowsPerSub, full, kEvictNormal);
+          if (!skip_n) tma_load_2d(sbase + Cfg::kOffN, &tmN, kc, t0, full, kEvictNormal);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
       if (p.dbg_cycles) {
         long long* o = p.dbg_cycles + (size_t)blockIdx.x * 8;
-        o[3] = clock64() - c_start; o[4] = c_empty;
+        o[3] = clk() - c_start; o[4] = c_empty;
       }
     }
   } else if (warp == 1) {
@@ -438,26 +454,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      long long c_acc = 0, c_ready = 0;
-      const long long c_start = clock64();
+      long long c_acc = 0, c_ready = 0, c_issue = 0, c_commit = 0;
+      const long long c_start = clk();
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = decode_item(p, item, kBlockT);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles);
         const int kb0 = w.kb0, kb1 = w.kb1;
         const uint32_t idesc = (w.t_cols == kBlockT) ? kIdesc : make_idesc(kFmt, 128 * kCG, (uint32_t)w.t_cols);
         const uint32_t idesc16 = make_idesc(kFmtBF16, 128 * kCG, (uint32_t)w.t_cols);  // cross16: the bf16 cross terms
-        long long c0 = clock64();
+        long long c0 = clk();
         if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
         else mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
-        c_acc += clock64() - c0;
+        c_acc += clk() - c0;
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
           // 3xTF32 / pairs: the ready barrier fires after the TMA barrier(s) and after the lo tiles are visible
-          c0 = clock64();
+          c0 = clk();
           if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_ready[stage]), phase);
           else mbar_wait(smem_u32(kUseReady ? &bar_ready[stage] : &bar_full[stage]), phase);
-          c_ready += clock64() - c0;
+          c_ready += clk() - c0;
           tc_fence_after();
+          c0 = clk();
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
           const uint32_t nbase = sbase + Cfg::kOffN;
           const int kvalid = min(kKE, p.K - kb * kKE);
@@ -504,7 +521,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             }
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          const long long c1 = clk();
+          c_issue += c1 - c0;
           if (kCG == 2) mma_commit_2cta(smem_u32(&bar_empty[stage])); else mma_commit(smem_u32(&bar_empty[stage]));
+          c_commit += clk() - c1;
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         // accumulator complete -> epilogue(s)
@@ -513,7 +533,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       }
       if (p.dbg_cycles) {
         long long* o = p.dbg_cycles + (size_t)blockIdx.x * 8;
-        o[0] = clock64() - c_start; o[1] = c_acc; o[2] = c_ready;
+        o[0] = clk() - c_start; o[1] = c_acc; o[2] = c_ready;
+        long long* o2 = p.dbg_cycles + (size_t)(gridDim.x + blockIdx.x) * 8;
+        o2[3] = c_issue; o2[4] = c_commit;
       }
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp) {
@@ -529,6 +551,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hempty[b]), ph ^ 1u);
           const uint32_t full = smem_u32(&bar_hfull[b]);
+          if (p.debug_flags & 128) { mbar_arrive(full); continue; }  // timing experiments: no H stream
           mbar_arrive_expect_tx(full, (uint32_t)Cfg::kHBufStride);
           tma_load_2d(ring + Cfg::kOffH + b * Cfg::kHBufStride, &tmH, n0, t0 + c * kHChunkT, full, kEvictFirst);
           if (kFro)
@@ -549,9 +572,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const int seq = hbase + c, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hready[b]), ph);
-          tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * Cfg::kHBufStride);
-          tma_store_commit();
-          tma_store_wait_read();
+          if (!(p.debug_flags & 128)) {
+            tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * Cfg::kHBufStride);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
           mbar_arrive(smem_u32(&bar_hempty[b]));
         }
         hbase += nch;
@@ -584,9 +609,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++seq) {
           // every warp observes every phase of the barrier (a waiter that skipped phases could be fooled by
           // parity aliasing two ring passes later); only the owner of the K-block does the work
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          mbar_wait_backoff(smem_u32(&bar_full[stage]), phase, EVC_SPLIT_SLEEP_NS);
           if (seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
-            const long long t1 = clock64();
+            const long long t1 = clk();
             if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
             if (!(p.debug_flags & 1)) {
               if (kCross16) split16_stage<Cfg, kMTiles>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
@@ -595,7 +620,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
             __syncwarp();
             if (lane == 0) ready_arrive(stage);
-            if (p.dbg_cycles && lane == 0) d_split += clock64() - t1;
+            if (p.dbg_cycles && lane == 0) d_split += clk() - t1;
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -615,7 +640,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     int acc = 0, stage = 0, hbase = 0, split_seq = 0;
     uint32_t acc_phase = 0, phase = 0;
     long long c_accfull = 0, c_hfull = 0, d_tma = 0, d_split = 0, d_n = 0;
-    const long long c_estart = clock64();
+    const long long c_estart = clk();
     for (int item = first_item; item < num_items; item += item_stride) {
       const WorkItem w = decode_item(p, item, kBlockT);
       const int m_group = w.m_group, split = w.split;
@@ -625,9 +650,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         // produce the lo tiles, one warp per K-block round-robin
         const int me = warp - 2;
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++split_seq) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);  // (all warps see all phases; see the dedicated warps)
+          mbar_wait_backoff(smem_u32(&bar_full[stage]), phase, EVC_SPLIT_SLEEP_NS);  // (all warps see all phases; see the dedicated warps)
           if (split_seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
-            const long long t1 = clock64();
+            const long long t1 = clk();
             if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
             if (!(p.debug_flags & 1)) {
               if (kCross16) split16_stage<Cfg, kMTiles>(ring_ptr + stage * Cfg::kStageBytes, lane, me % kWarpsPerStage);
@@ -636,14 +661,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ready_arrive(stage);
-            if (p.dbg_cycles && lane == 0) d_split += clock64() - t1;
+            if (p.dbg_cycles && lane == 0) d_split += clk() - t1;
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
-      long long c0 = clock64();
-      mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
-      c_accfull += clock64() - c0;
+      long long c0 = clk();
+      mbar_wait_backoff(smem_u32(&bar_acc_full[acc]), acc_phase, EVC_EPI_SLEEP_NS);
+      c_accfull += clk() - c0;
       tc_fence_after();
       if (kStageH) {
         // ---- fused multiplicative update through the shared-memory H chunks ----
@@ -657,9 +682,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockT + c * 32), v);
-          c0 = clock64();
+          c0 = clk();
           mbar_wait(smem_u32(&bar_hfull[b]), ph);
-          c_hfull += clock64() - c0;
+          c_hfull += clk() - c0;
           float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * Cfg::kHBufStride) + quarter * 32 + lane;
           float h[32];
 #pragma unroll
@@ -767,7 +792,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     }
     if (p.dbg_cycles && warp == 2 && lane == 0) {
       long long* o = p.dbg_cycles + (size_t)blockIdx.x * 8;
-      o[5] = clock64() - c_estart; o[6] = c_accfull; o[7] = c_hfull;
+      o[5] = clk() - c_estart; o[6] = c_accfull; o[7] = c_hfull;
     }
     if (p.dbg_cycles && lane == 0 && kSplit3 && !Cfg::kDedicatedXform) {
       unsigned long long* o = reinterpret_cast<unsigned long long*>(p.dbg_cycles + (size_t)(gridDim.x + blockIdx.x) * 8);
@@ -1074,6 +1099,11 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
             a[5] / nl, a[6] / nl, a[7] / nl);
     double tma = 0, spl = 0, cnt = 0;
     for (int b = 0; b < grid; ++b) { tma += (double)h[(size_t)(grid + b) * 8]; spl += (double)h[(size_t)(grid + b) * 8 + 1]; cnt += (double)h[(size_t)(grid + b) * 8 + 2]; }
+    {
+      double iss = 0, com = 0;
+      for (int b = 0; b < grid; b += kCG) { iss += (double)h[(size_t)(grid + b) * 8 + 3]; com += (double)h[(size_t)(grid + b) * 8 + 4]; }
+      fprintf(stderr, "[evc timing]    MMA thread: issuing MMAs %.0f cycles, commits %.0f cycles (leaders avg)\n", iss / nl, com / nl);
+    }
     if (cnt > 0) fprintf(stderr, "[evc timing]    per K-block: TMA issue -> landed %.0f cycles, landed -> split done + ready arrive %.0f cycles (%.0f blocks)\n", tma / cnt, spl / cnt, cnt);
     ++prints;
   }

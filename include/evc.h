@@ -49,7 +49,8 @@ enum evc_status {
 /* Arithmetic of the two contractions A*H and A^T*R (and of Y = B*H). */
 enum evc_mode {
   EVC_MODE_FP32 = 0,   /* fp32 FFMA on CUDA cores: exact fp32, any shape (also F = 1, the f0 track) */
-  EVC_MODE_3XTF32 = 1, /* tcgen05 kind::tf32, hi/lo split of both operands, 3 MMAs per product: fp32-accurate */
+  EVC_MODE_3XTF32 = 1, /* fp32-accurate: hi/lo split of both operands in shared memory; hi*hi on tcgen05 kind::tf32,
+                          the two cross terms on kind::f16 (bf16 copies of hi and lo), lo*lo dropped            */
   EVC_MODE_TF32 = 2,   /* tcgen05 kind::tf32, one MMA per product: fast mode                           */
   EVC_MODE_BF16 = 3    /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate): fast mode                */
 };
@@ -183,6 +184,12 @@ double evc_last_enqueue_ms(void);
 
 /* Diagnostics: number of kernels this library has launched in this process. */
 long long evc_kernel_launch_count(void);
+
+/* Diagnostics: tensor-core passes one logical product costs in `mode`, in units of a dense MMA pass of the mode's
+ * roofline type: EVC_MODE_3XTF32 -> 2 (TF32 hi*hi + two BF16 cross-term MMAs, each worth half a TF32 pass; 3 when
+ * EVC_SPLIT_CROSS16=0 selects three TF32 MMAs), EVC_MODE_TF32 / EVC_MODE_BF16 -> 1, EVC_MODE_FP32 -> 0 (no tensor
+ * cores).  bench.py multiplies the algorithmic TFLOP/s by this to get the executed figure ncu's tensor pipe sees. */
+int evc_mma_passes_per_product(int mode);
 
 /*
  * Diagnostics: per-kernel-class device timing.  After evc_profile_enable(d, 1) every launch of the handle is
