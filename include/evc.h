@@ -52,7 +52,8 @@ enum evc_mode {
   EVC_MODE_3XTF32 = 1, /* fp32-accurate: hi/lo split of both operands in shared memory; hi*hi on tcgen05 kind::tf32,
                           the two cross terms on kind::f16 (bf16 copies of hi and lo), lo*lo dropped            */
   EVC_MODE_TF32 = 2,   /* tcgen05 kind::tf32, one MMA per product: fast mode                           */
-  EVC_MODE_BF16 = 3    /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate): fast mode                */
+  EVC_MODE_BF16 = 3    /* tcgen05 kind::f16 on bf16 copies of A, of the ratio and of H (shadow kept by the fused
+                          update), fp32 accumulate and fp32 multiplicative update: fastest, ~1e-3 on H     */
 };
 
 enum evc_loss {

@@ -58,5 +58,6 @@ if __name__ == "__main__":
     if "stacked" in which:
         run("context_stacked_50k", 2565, 50000, 1000, "3xtf32", iters=10)
         run("context_stacked_50k", 2565, 50000, 1000, "tf32", iters=10)
+        run("context_stacked_50k", 2565, 50000, 1000, "bf16", iters=10)
     if "large" in which:
         run("large_dictionary_200k(1gpu)", 513, 200000, 2000, "3xtf32", iters=6)
