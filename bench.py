@@ -328,7 +328,9 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if exemplar_sharded else "weak", "vs_baseline": None,
-                "dtype": {"3xtf32": "tf32x3 (fp32-accurate)", "tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.mode],
+                "dtype": {"3xtf32": ("tf32 hi*hi + 2x bf16 cross terms (fp32-accurate split)" if passes == 2
+                                     else "tf32x3 (fp32-accurate split)"),
+                          "tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.mode],
                 "data": "synthetic",
                 "config": {"workload": wl.name, "F": wl.F, "N": wl.N, "T": wl.T, "iterations": wl.iterations,
                            "mode": args.mode, "sharding": ("exemplar" if exemplar_sharded else "utterance") if world > 1 else "none",
