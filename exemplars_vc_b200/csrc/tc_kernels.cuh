@@ -335,7 +335,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   // cycle counter of the EVC_DEBUG_TIMING instrumentation: not read at all in normal runs (a CS2R per pipeline step
   // of the single-thread roles is not free)
   const bool dbg_on = p.dbg_cycles != nullptr;
-auto clk = [dbg_on]() -> long long { return dbg_on ? clock64() : 0ll; };
+  auto clk = [dbg_on]() -> long long { return dbg_on ? clock64() : 0ll; };
+  const long long t_entry = clk();
   const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
   uint8_t* ring_ptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t ring = smem_u32(ring_ptr);
@@ -371,8 +372,10 @@ auto clk = [dbg_on]() -> long long { return dbg_on ? clock64() : 0ll; };
   const uint32_t tmem_base = tmem_base_smem;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous
   // kernel in the stream; from here on its results are needed
+  const long long t_setup = clk();
   pdl_wait();
   pdl_launch_dependents();
+  const long long t_go = clk();
 
   const int num_items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
   const int first_item = blockIdx.x / kCG, item_stride = gridDim.x / kCG;  // both CTAs of a pair walk the same items
@@ -827,6 +830,11 @@ auto clk = [dbg_on]() -> long long { return dbg_on ? clock64() : 0ll; };
     __syncwarp();
     tc_fence_after();
     if (kCG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    if (p.dbg_cycles && lane == 0) {
+      // CTA lifetime: entry -> barriers/TMEM set up -> predecessor grid done (PDL) -> ... -> TMEM released
+      long long* o2 = p.dbg_cycles + (size_t)(gridDim.x + blockIdx.x) * 8;
+      o2[5] = t_setup - t_entry; o2[6] = t_go - t_setup; o2[7] = clk() - t_entry;
+    }
   }
 }
 
@@ -1122,6 +1130,15 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
       double iss = 0, com = 0;
       for (int b = 0; b < grid; b += kCG) { iss += (double)h[(size_t)(grid + b) * 8 + 3]; com += (double)h[(size_t)(grid + b) * 8 + 4]; }
       fprintf(stderr, "[evc timing]    MMA thread: issuing MMAs %.0f cycles, commits %.0f cycles (leaders avg)\n", iss / nl, com / nl);
+    }
+    {
+      double su = 0, pw = 0, life = 0, lmax = 0;
+      for (int b = 0; b < grid; ++b) {
+        su += (double)h[(size_t)(grid + b) * 8 + 5]; pw += (double)h[(size_t)(grid + b) * 8 + 6];
+        life += (double)h[(size_t)(grid + b) * 8 + 7]; lmax = std::max(lmax, (double)h[(size_t)(grid + b) * 8 + 7]);
+      }
+      fprintf(stderr, "[evc timing]    CTA lifetime (all CTAs): set-up %.0f cycles, PDL wait %.0f, total avg %.0f max %.0f\n",
+              su / grid, pw / grid, life / grid, lmax);
     }
     if (cnt > 0) fprintf(stderr, "[evc timing]    per K-block: TMA issue -> landed %.0f cycles, landed -> split done + ready arrive %.0f cycles (%.0f blocks)\n", tma / cnt, spl / cnt, cnt);
     ++prints;
