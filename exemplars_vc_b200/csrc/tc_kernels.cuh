@@ -152,6 +152,12 @@ constexpr int kSmemBudget = 227 * 1024 - 2048;
 // MMA-issuing thread, per K-block (A/B knobs, both measured and rejected: 113.3 vs 109.9 us for contraction 2):
 // EVC_KLOOP_FENCE 0 drops the tcgen05.fence::after_thread_sync after every stage wait, EVC_KLOOP_PEEK 1 polls the
 // NEXT stage's barrier before issuing this stage's MMAs.
+// EVC_EARLY_HIHI 1 (cross16 only): the tf32 hi*hi MMAs of a K-block are issued as soon as its TMA bytes have
+// landed in both CTAs ("landed" barrier), the bf16 cross terms when the split warps are done ("ready"), so the
+// split overlaps tensor work of the same stage instead of preceding it.
+#ifndef EVC_EARLY_HIHI
+#define EVC_EARLY_HIHI 0
+#endif
 #ifndef EVC_KLOOP_FENCE
 #define EVC_KLOOP_FENCE 1
 #endif
@@ -314,6 +320,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   constexpr int kKStep = kBf16 ? 16 : 8;              // K elements per MMA (32 bytes either way)
   constexpr uint32_t kIdesc = make_idesc(kFmt, 128 * kCG, kBlockT);
   constexpr bool kCross16 = (kSplit3 == 2);
+  constexpr bool kEarly = kCross16 && (EVC_EARLY_HIHI != 0);
   // does the MMA warp wait on the "ready" barrier (split and/or pair) or directly on the TMA barrier?
   constexpr bool kUseReady = kSplit3 || kCG == 2;
 
@@ -321,6 +328,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_full[kStages];   // this CTA's TMA bytes landed
   __shared__ __align__(8) uint64_t bar_ready[kStages];  // (leader's copy is used) stage usable by the MMA: lo tiles
                                                         // written / both CTAs of the pair loaded
+  __shared__ __align__(8) uint64_t bar_landed[kStages];  // (leader's copy is used) the TMA bytes of the stage landed in
+                                                         // every CTA of the pair (EVC_EARLY_HIHI)
   __shared__ __align__(8) uint64_t bar_empty[kStages];  // MMAs that read the stage retired (both CTAs' copies fire)
   __shared__ __align__(8) uint64_t bar_acc_full[kAccStages];
   __shared__ __align__(8) uint64_t bar_acc_empty[kAccStages];  // (leader's copy is used)
@@ -349,6 +358,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), 1);
       mbar_init(smem_u32(&bar_ready[i]), Cfg::kReadyArrivals * kCG);
+      mbar_init(smem_u32(&bar_landed[i]), kCG);
       mbar_init(smem_u32(&bar_empty[i]), 1);
     }
     for (int i = 0; i < kAccStages; ++i) {
@@ -384,6 +394,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   auto ready_arrive = [&](int stage) {
     if (kCG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&bar_ready[stage]), 0));
     else mbar_arrive(smem_u32(&bar_ready[stage]));
+  };
+
+  auto landed_arrive = [&](int stage) {
+    if (kCG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&bar_landed[stage]), 0));
+    else mbar_arrive(smem_u32(&bar_landed[stage]));
   };
 
   if (warp == 0) {
@@ -483,7 +498,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           // 3xTF32 / pairs: the ready barrier fires after the TMA barrier(s) and after the lo tiles are visible
           c0 = clk();
-          if (!peeked) {
+          if (kEarly) {
+            if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_landed[stage]), phase);
+            else mbar_wait(smem_u32(&bar_landed[stage]), phase);
+          } else if (!peeked) {
             if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_ready[stage]), phase);
             else mbar_wait(smem_u32(kUseReady ? &bar_ready[stage] : &bar_full[stage]), phase);
           }
@@ -506,7 +524,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             if (m0 + i * Cfg::kRowsPerSub >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
             if (p.debug_flags & 2) break;
             const uint32_t d = tmem_base + (uint32_t)((acc * kMTiles + i) * kBlockT);
-            if (kCross16) {
+            if (kEarly) {
+              // hi*hi now (only needs the TMA bytes); the cross terms of all sub-tiles follow below, after "ready"
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t a_hi = make_smem_desc(sbase + i * Cfg::kMTileBytes + ks * 32, Cfg::kRowBytes);
+                const uint64_t b_hi = make_smem_desc(nbase + ks * 32, Cfg::kRowBytes);
+                mma_issue<false, kCG>(d, a_hi, b_hi, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+              }
+            } else if (kCross16) {
               // small terms first: lo16*hi16 + hi16*lo16 over the whole K-block (one 16-element bf16 MMA each;
               // a K tail was zero-filled by TMA), then hi*hi in tf32
               const uint32_t a16 = sbase + Cfg::kOffMlo + i * Cfg::kMTileBytes, b16 = nbase + Cfg::kNTileBytes;
@@ -540,6 +565,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
               } else {
                 mma_issue<kBf16, kCG>(d, a_hi, b_hi, idesc, accum);
               }
+            }
+          }
+          if (kEarly) {
+            const long long cw = clk();
+            if (kCG == 2) mbar_wait_cluster(smem_u32(&bar_ready[stage]), phase);
+            else mbar_wait(smem_u32(&bar_ready[stage]), phase);
+            c_ready += clk() - cw;
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < kMTiles; ++i) {
+              if (m0 + i * Cfg::kRowsPerSub >= p.M_total) break;
+              if (p.debug_flags & 2) break;
+              const uint32_t d = tmem_base + (uint32_t)((acc * kMTiles + i) * kBlockT);
+              const uint32_t a16 = sbase + Cfg::kOffMlo + i * Cfg::kMTileBytes, b16 = nbase + Cfg::kNTileBytes;
+              mma_issue<true, kCG>(d, make_smem_desc(a16 + Cfg::kMTileBytes / 2, 32), make_smem_desc(b16, 32), idesc16, 1u);
+              mma_issue<true, kCG>(d, make_smem_desc(a16, 32), make_smem_desc(b16 + Cfg::kNTileBytes / 2, 32), idesc16, 1u);
             }
           }
           // frees the smem slot (in both CTAs of a pair) when these MMAs retire
@@ -632,6 +673,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           // every warp observes every phase of the barrier (a waiter that skipped phases could be fooled by
           // parity aliasing two ring passes later); only the owner of the K-block does the work
           mbar_wait_backoff(smem_u32(&bar_full[stage]), phase, EVC_SPLIT_SLEEP_NS);
+          if (kEarly && me == 0 && lane == 0) landed_arrive(stage);
           if (seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
             const long long t1 = clk();
             if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
@@ -673,6 +715,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int me = warp - 2;
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++split_seq) {
           mbar_wait_backoff(smem_u32(&bar_full[stage]), phase, EVC_SPLIT_SLEEP_NS);  // (all warps see all phases; see the dedicated warps)
+          if (kEarly && me == 0 && lane == 0) landed_arrive(stage);
           if (split_seq % Cfg::kSplitGroups == me / kWarpsPerStage) {
             const long long t1 = clk();
             if (p.dbg_cycles && lane == 0) { d_tma += t1 - dbg_t_issue[stage]; ++d_n; }
