@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--iterations", type=int, default=None, help="override the workload's iteration count")
     ap.add_argument("--ref-sample-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-float64", action="store_true", help="skip the float64 leg of the CPU baseline")
     ap.add_argument("--no-p2p", action="store_true", help="exemplar sharding: ncclAllReduce instead of the peer-memory kernel")
     args = ap.parse_args()
 
@@ -349,6 +350,12 @@ def main():
                 "sample": f"{args.ref_sample_iters} of {wl.iterations} KL iterations of the reference's sklearn call "
                           f"(float32) at the full shape, extrapolated linearly, + np.matmul for Y",
                 "s_per_iteration": per_iter}
+            if not args.no_cpu_float64:
+                # the reference's WORLD branch is float64 (SURVEY 8d asks for both); a shorter sample keeps the run bounded
+                n64 = max(2, args.ref_sample_iters // 2)
+                secs64, per_iter64 = reference_step_seconds(X_host, A_h, B_h, wl.iterations, n64, np.float64)
+                line["cpu_baseline"].update(value_float64=wl.T / secs64, s_per_iteration_float64=per_iter64,
+                                            sample_float64=f"{n64} of {wl.iterations} iterations, float64")
         print(json.dumps(line))
     d.close()
     if world > 1:
