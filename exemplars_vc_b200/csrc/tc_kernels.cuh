@@ -97,7 +97,7 @@ struct WorkItem {
   int m_group, t_tile, split, kb0, kb1;
   int t_off, t_cols;  // frame offset inside the frame tile and number of frame columns of this item
 };
-__device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item, int block_t) {
+__host__ __device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item, int block_t) {
   WorkItem w;
   w.t_off = 0;
   w.t_cols = block_t;

@@ -98,3 +98,22 @@ def test_script_level_signatures():
     assert list(inspect.signature(NMF.fit_transform).parameters)[:5] == ["self", "X", "r_components", "initW", "givenW"]
     with pytest.raises(NotImplementedError):
         NMF().fit_transform(np.ones((3, 2)), 2, False, 0)
+
+
+def test_work_decomposition_of_both_contractions(tmp_path):
+    """tests/host/plan_check.cu (host-only, no GPU): for the BASELINE shapes and 3000 random ones, plan_c1 +
+    decode_item give every (row group, frame tile) its whole K range exactly once, no work item is empty, split
+    indices stay inside the partial buffer, and the half-width tail items of contraction 2 tile each frame tile."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "plan_check")
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                    os.path.join(root, "tests", "host", "plan_check.cu"), "-ldl"], check=True)
+    for cg in ("2", "1"):
+        r = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, EVC_CTA_GROUP=cg))
+        assert r.returncode == 0 and " 0 failures" in r.stdout, r.stdout[-2000:]
