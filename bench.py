@@ -319,7 +319,11 @@ def main():
                     "frac": achieved / tf32_peak, "traffic": traffic,
                     "peak_source": ("dense BF16 = bf16_tflops_sustained, " if args.mode == "bf16" else
                                     "dense TF32 = 1/2 of bf16_tflops_sustained, ") + peaks["_source"],
-                    "executed_tflops": achieved * passes, "executed_frac": achieved * passes / tf32_peak,
+                    # what the tensor pipe executes: `passes` MMAs per product, bf16 (kind::f16) MMAs in the
+                    # fp32-accurate split mode and in bf16 mode, tf32 MMAs in tf32 mode
+                    "executed_tflops": achieved * passes,
+                    "executed_frac": achieved * passes / (tf32_peak if args.mode == "tf32" else peaks["bf16_tflops_sustained"]),
+                    "executed_peak": "dense TF32" if args.mode == "tf32" else "dense BF16 (bf16_tflops_sustained)",
                     "mma_passes_per_product": passes, "library_gemm_this_run": lib_gemm,
                     "us_per_launch": per_launch_s * 1e6,
                     "step_share": {k: round(v[0] / max(sum(x[0] for x in prof.values()), 1e-9), 4) for k, v in prof.items()},
@@ -329,8 +333,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if exemplar_sharded else "weak", "vs_baseline": None,
-                "dtype": {"3xtf32": ("tf32 hi*hi + 2x bf16 cross terms (fp32-accurate split)" if passes == 2
-                                     else "tf32x3 (fp32-accurate split)"),
+                "dtype": {"3xtf32": "bf16x3 split products, fp32 accumulate (fp32-accurate mode)",
                           "tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.mode],
                 "data": "synthetic",
                 "config": {"workload": wl.name, "F": wl.F, "N": wl.N, "T": wl.T, "iterations": wl.iterations,

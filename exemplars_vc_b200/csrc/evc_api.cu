@@ -303,7 +303,8 @@ const char* evc_last_error_string(void) { return g_err; }
 long long evc_kernel_launch_count(void) { return g_launches.load(); }
 double evc_last_enqueue_ms(void) { return g_last_enqueue_ms; }
 int evc_mma_passes_per_product(int mode) {
-  if (mode == EVC_MODE_3XTF32) return tc::split_flavor() == 2 ? 2 : 3;
+  // MMAs issued per product: 3 bf16 (kind::f16) MMAs in the fp32-accurate split mode, 1 in the fast modes
+  if (mode == EVC_MODE_3XTF32) return 3;
   return (mode == EVC_MODE_TF32 || mode == EVC_MODE_BF16) ? 1 : 0;
 }
 

@@ -46,21 +46,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-// Same, for waits that are not on the critical path or are executed by many warps at once (split warps watching a
-// ring stage, epilogue warps waiting for an accumulator): sleep between polls so the spinning does not compete
-// with the operand traffic for the shared-memory pipe.
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (ns) __nanosleep(ns);
-    if (clock64() - t0 > 4000000000ll) {
-      printf("evc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -133,6 +118,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+
+// Same load issued by a CTA of a pair (cta_group::2): the data lands in THIS CTA's shared memory, the transaction
+// bytes are credited to `bar_cluster`, a shared::cluster address that may name the LEADER CTA's barrier (mapa_rank),
+// so the MMA-issuing thread waits on one barrier for both halves of a stage -- no relay warp, no remote arrive.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* m, int c0, int c1,
+                                                 uint32_t bar_cluster, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 

@@ -50,7 +50,7 @@ def contraction_errors(mode, F, N, T, seed=1):
 def main():
     print(torch.cuda.get_device_name(0), torch.version.cuda)
     shapes = [(13, 32, 8), (64, 128, 32), (201, 777, 37), (513, 2000, 64), (513, 20000, 1000), (600, 4100, 300)]
-    for mode in ("fp32", "tf32", "3xtf32"):
+    for mode in ("fp32", "tf32", "bf16", "3xtf32"):
         for (F, N, T) in shapes:
             if mode == "fp32" and N * T > 4e6:
                 continue
@@ -62,7 +62,7 @@ def main():
     # timing of the headline config, per mode
     A, B = synth.dictionaries(synth.BASE_SEED + 1, 513, 20000)
     X = synth.frames(synth.BASE_SEED + 1, A, 1000)
-    for mode in ("tf32", "3xtf32"):
+    for mode in ("tf32", "bf16", "3xtf32"):
         try:
             with ExemplarDictionary(A, B, mode=mode) as d:
                 d.solve(X, tol=0.0, max_iter=5)

@@ -41,12 +41,11 @@ def test_version_defaults_and_struct_layout(built_lib):
 
 
 def test_mma_passes_per_product_is_reported(built_lib):
-    """bench.py's executed-TFLOP/s figure comes from the library: 2 passes for the fp32-accurate split (TF32 hi*hi +
-    two BF16 cross-term MMAs worth half a pass each), 1 for the fast modes, 0 for the FFMA mode."""
+    """bench.py's executed-TFLOP/s figure comes from the library: 3 bf16 MMAs per product in the fp32-accurate split
+    mode (x = x1 + x2 in bf16, three of the four partial products), 1 MMA in the fast modes, 0 for the FFMA mode."""
     from exemplars_vc_b200 import _lib
     L = _lib.lib()
-    want_accurate = 3 if os.environ.get("EVC_SPLIT_CROSS16") == "0" else 2
-    assert L.evc_mma_passes_per_product(_lib.MODE_3XTF32) == want_accurate
+    assert L.evc_mma_passes_per_product(_lib.MODE_3XTF32) == 3
     assert L.evc_mma_passes_per_product(_lib.MODE_TF32) == 1
     assert L.evc_mma_passes_per_product(_lib.MODE_BF16) == 1
     assert L.evc_mma_passes_per_product(_lib.MODE_FP32) == 0
