@@ -25,6 +25,7 @@ struct evc_comm {
 
 struct evc_dict {
   int F = 0, N = 0, mode = 0, device = 0;
+  int mode_requested = 0;  // what the caller asked for; `mode` is what runs (problems below one MMA tile -> FFMA)
   int n_total = 0;  // exemplars across all shards (== N when not sharded): H0 uses it (sklearn n_components)
   bool has_target = false;
   // fp32 mode operands
@@ -49,6 +50,7 @@ struct evc_dict {
 namespace {
 
 thread_local double g_last_enqueue_ms = 0.0;
+constexpr int kMinTensorF = 64, kMinTensorN = 128;
 
 // A*H of the current activations.  With the peer-memory all-reduce attached it lives in the IPC exchange buffer
 // (the reduced result lands there directly); otherwise in the handle's own workspace.
@@ -345,6 +347,11 @@ int evc_dict_create(const float* A, int ldA, const float* B, int ldB, int F, int
   cudaStream_t s = (cudaStream_t)stream;
   evc_dict* d = new (std::nothrow) evc_dict();
   if (!d) return fail(EVC_ERR_CUDA, "evc_dict_create: out of host memory");
+  d->mode_requested = mode;
+  // A problem that does not fill one 128 x 64 operand tile (the F = 1 f0 track of 04_align_n_nmf.py:288, toy cases)
+  // gains nothing from the tensor cores and leaves the split products too few terms to average their rounding:
+  // it runs on the exact-fp32 CUDA-core kernels whatever tensor-core mode was asked for.
+  if (mode != EVC_MODE_FP32 && (F < kMinTensorF || N < kMinTensorN)) mode = EVC_MODE_FP32;
   d->F = F; d->N = N; d->n_total = N; d->mode = mode; d->has_target = (B != nullptr);
   int st = [&]() -> int {
     EVC_CUDA(cudaGetDevice(&d->device));
@@ -391,7 +398,7 @@ int evc_dict_info(evc_dict_t d, int* F, int* N, int* mode, int* has_target) {
   if (!d) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dict_info: null handle");
   if (F) *F = d->F;
   if (N) *N = d->N;
-  if (mode) *mode = d->mode;
+  if (mode) *mode = d->mode;  // the mode that runs
   if (has_target) *has_target = d->has_target ? 1 : 0;
   return EVC_OK;
 }
@@ -466,7 +473,7 @@ int evc_factorize_convert_host(evc_dict_t d, const float* X, int ldX, int T, flo
   if (p->init == EVC_INIT_GIVEN && !H) return fail(EVC_ERR_INVALID_ARGUMENT, "init = GIVEN needs H");
   if (T == 0) return EVC_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int ldXd = round_up(d->F, 4), ldHd = round_up(d->N, 4), ldYd = round_up(d->F, 4);
+  const int ldXd = round_up(d->F, 4), ldHd = round_up(d->N, 32), ldYd = round_up(d->F, 4);
   float *dX = nullptr, *dH = nullptr, *dY = nullptr;
   int st = [&]() -> int {
     EVC_CUDA(cudaMalloc(&dX, (size_t)T * ldXd * sizeof(float)));

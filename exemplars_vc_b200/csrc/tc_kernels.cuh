@@ -46,7 +46,11 @@ namespace tc {
 
 using namespace umma;
 
-inline int k_pitch(int F) { return round_up(F, 8); }
+// Row pitch (elements) of every K-major operand: a multiple of 128 bytes, so that no 64- or 128-byte row segment a
+// TMA box fetches straddles a 128-byte L2 line (a 1056-byte pitch cost contraction 2 25 % extra L2->SM traffic:
+// profiles/r2b_*).
+inline int k_pitch(int F) { return round_up(F, 32); }
+inline int k_pitch16(int F) { return round_up(F, 64); }
 
 enum TcEpilogue { TEPI_PARTIAL = 0, TEPI_MU_KL = 1, TEPI_MU_FRO = 2 };
 enum TcPrec { PREC_SPLIT = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
@@ -80,7 +84,17 @@ struct GemmParams {
   int left_lda, n_left;
   float* left_out;      // [l][t][row] partial sums, row = 4*(128-exemplar block) + lane quarter
   int left_ld, left_rows;  // frames pitch, rows pitch
+  int debug_flags;      // -DEVC_INSTRUMENT builds only (tools/flag_sweep.sh); always 0 and never read otherwise
 };
+
+// Timing experiments (results are garbage when a flag is set).  The default build compiles every test to `false`.
+//   1 no plane split (contraction 1)   2 no MMA issue   4 no operand TMA   8 no update arithmetic in the epilogue
+//  16 no H chunk loads / stores       32 no leftover-row partials        64 no TMEM loads
+#ifdef EVC_INSTRUMENT
+#define EVC_DBG(p, bit) (((p).debug_flags & (bit)) != 0)
+#else
+#define EVC_DBG(p, bit) false
+#endif
 
 // vals[j] (j = 0..31) per lane -> returns, in lane L, the sum over all 32 lanes of vals[L]  (31 shuffles).
 __device__ __forceinline__ float warp_transpose_sum(float (&vals)[32], int lane) {
@@ -145,7 +159,13 @@ constexpr int kSmemBudget = 227 * 1024 - 2048;
 // The fused-update epilogue stages H through shared memory in [32 frames x 128 exemplars] chunks moved by TMA
 // (loads prefetched by a loader warp, stores issued by a storer warp): per-lane 128-byte global accesses
 // from the epilogue warps were limited by the SM's outstanding-miss capacity, bulk copies are not.
-constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = 4;
+#ifndef EVC_H_BUFS
+#define EVC_H_BUFS 4
+#endif
+#ifndef EVC_MAX_STAGES
+#define EVC_MAX_STAGES 8
+#endif
+constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = EVC_H_BUFS;
 
 template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, bool kStageH, bool kStageQ>
 struct TileCfg {
@@ -171,7 +191,7 @@ struct TileCfg {
   static constexpr int kHBufStride = kStageQ ? 2 * kHBufBytes : kHBufBytes;
   static constexpr int kHBytes = kStageH ? kHBufs * kHBufBytes : 0;
   static constexpr int kStagesRaw = (kSmemBudget - kHBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > EVC_MAX_STAGES ? EVC_MAX_STAGES : kStagesRaw;
   static constexpr int kAccCols = kMTiles * kBlockT;
   static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
   static constexpr int kLoaderWarp = 2 + kEpiWarps;  // H chunk loader, then storer
@@ -310,6 +330,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = full_leader + (uint32_t)stage * 8u;
+          if (EVC_DBG(p, 4)) {
+            if (rank == 0) mbar_arrive(smem_u32(&bar_full[stage]));
+            if (kSplitN) mbar_arrive(smem_u32(&bar_raw[stage]));
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           // the leader expects both CTAs' bytes (boxes past the matrix edge are zero-filled and still counted)
           if (rank == 0) mbar_arrive_expect_tx(smem_u32(&bar_full[stage]), (uint32_t)(kCG * Cfg::kTxBytes));
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
@@ -323,7 +349,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           if (kSplitN) {
             const uint32_t rawb = smem_u32(&bar_raw[stage]);
             mbar_arrive_expect_tx(rawb, (uint32_t)Cfg::kRawBytes);
-            tma_load_2d(sbase + Cfg::kOffRaw, &tmN, kc, t0, rawb, kEvictNormal);
+            tma_load_2d(sbase + Cfg::kOffRaw, &tmN, kc, t0, rawb, kEvictFirst);  // H is streamed: keep A^T in L2
           } else {
 #pragma unroll
             for (int pl = 0; pl < Cfg::kPlanes; ++pl)
@@ -356,6 +382,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i) {
             if (m0 + i * Cfg::kRowsPerSub >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
+            if (EVC_DBG(p, 2)) break;
             const uint32_t d = tmem_base + (uint32_t)((acc * kMTiles + i) * kBlockT);
             const uint32_t abase = sbase + i * Cfg::kPlanes * Cfg::kMPlaneBytes;
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -398,6 +425,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hempty[b]), ph ^ 1u);
           const uint32_t full = smem_u32(&bar_hfull[b]);
+          if (EVC_DBG(p, 16)) { mbar_arrive(full); continue; }
           mbar_arrive_expect_tx(full, (uint32_t)Cfg::kHBufStride);
           tma_load_2d(ring + Cfg::kOffH + b * Cfg::kHBufStride, &tmH, n0, t0 + c * kHChunkT, full, kEvictFirst);
           if (kFro)
@@ -418,9 +446,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const int seq = hbase + c, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hready[b]), ph);
-          tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * Cfg::kHBufStride);
-          tma_store_commit();
-          tma_store_wait_read();
+          if (!EVC_DBG(p, 16)) {
+            tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * Cfg::kHBufStride);
+            tma_store_commit();
+            tma_store_wait_read();
+          }
           mbar_arrive(smem_u32(&bar_hempty[b]));
         }
         hbase += nch;
@@ -447,7 +477,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(smem_u32(&bar_raw[stage]), phase);
           uint8_t* sb = ring_ptr + stage * Cfg::kStageBytes;
-          split_planes<Cfg::kNRows>(sb + Cfg::kOffRaw, sb + Cfg::kOffN, sb + Cfg::kOffN + Cfg::kNPlaneBytes, tid);
+          if (!EVC_DBG(p, 1))
+            split_planes<Cfg::kNRows>(sb + Cfg::kOffRaw, sb + Cfg::kOffN, sb + Cfg::kOffN + Cfg::kNPlaneBytes, tid);
           fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(full_leader + (uint32_t)stage * 8u);
@@ -461,12 +492,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int m = m_group * Cfg::kRowsPerSub + (int)rank * 128 + quarter * 32 + lane;
         float den = ((m < p.M_total && !kFro) ? p.colsum[m] : 1.f) + p.lam;
         if (den == 0.f) den = p.eps;
+        // this lane's entries of the leftover dictionary rows (n_left <= 8)
+        float la[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) la[l] = (l < p.n_left && m < p.M_total) ? p.left_a[(size_t)l * p.left_lda + m] : 0.f;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = half; c < nch; c += 2) {
           const int seq = hbase + c, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockT + c * 32), v);
+          if (!EVC_DBG(p, 64))
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockT + c * 32), v);
           mbar_wait(smem_u32(&bar_hfull[b]), ph);
           float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * Cfg::kHBufStride) + quarter * 32 + lane;
           float h[32];
@@ -474,7 +510,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) h[j] = hb[j * 128];
           tmem_ld_wait();
           const int tbm = t0 + c * 32;
-          if (kFro) {
+          if (EVC_DBG(p, 8)) {
+            // (timing experiments: activations pass through unchanged)
+          } else if (kFro) {
             // Frobenius: H <- H * (X A^T) / (A^T (A H) + lambda); the numerator chunk sits behind the H chunk
             const float* qb = hb + kHBufBytes / 4;
 #pragma unroll
@@ -507,9 +545,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA store
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_hready[b]));
-          for (int l = 0; l < p.n_left; ++l) {
+#pragma unroll
+          for (int l = 0; l < 8; ++l) {
+            if (l >= p.n_left || EVC_DBG(p, 32)) break;
             // (rows past T and exemplars past N were zero-filled by TMA: they add nothing)
-            const float a = (m < p.M_total) ? p.left_a[(size_t)l * p.left_lda + m] : 0.f;
+            const float a = la[l];
             float sv[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) sv[j] = h[j] * a;
@@ -844,7 +884,14 @@ inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUten
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 2 : 1;
+#ifdef EVC_INSTRUMENT
+  static const int dbg = getenv("EVC_DEBUG_FLAGS") ? atoi(getenv("EVC_DEBUG_FLAGS")) : 0;
+  GemmParams q = p;
+  q.debug_flags = dbg;
+  EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, q));
+#else
   EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, p));
+#endif
   EVC_LAUNCH_CHECK();
   return EVC_OK;
 }
@@ -932,7 +979,7 @@ inline int build_operands(DictOperands* o, int mode, const float* A, const float
   }
   const int planes = (mode == EVC_MODE_3XTF32) ? 2 : 1;
   const int bk = bk_elems(mode);
-  o->ldA16 = round_up(F, 8); o->ldN16 = round_up(N, 8);
+  o->ldA16 = k_pitch16(F); o->ldN16 = k_pitch16(N);
   o->a_rows = plane_rows(N); o->at_rows = plane_rows(o->F_main);
   const size_t a_elems = (size_t)o->a_rows * o->ldA16, at_elems = (size_t)o->at_rows * o->ldN16;
   EVC_CUDA(cudaMalloc(&o->A16, planes * a_elems * sizeof(__nv_bfloat16)));

@@ -202,7 +202,7 @@ class ExemplarDictionary:
             if offs[0] != 0 or offs[-1] != T:
                 raise ValueError("t_offsets must start at 0 and end at the number of stacked frames")
             n_utt = len(offs) - 1
-            ldH = _round_up(self.N, 4)
+            ldH = _round_up(self.N, 32)      # 128-byte row pitch: TMA row segments never straddle an L2 line
             Hbuf = torch.empty((max(T, 1), ldH), dtype=torch.float32, device=self.device)
             H = Hbuf[:T, : self.N]
             if H0 is not None:
@@ -231,7 +231,7 @@ class ExemplarDictionary:
                 raise ValueError(f"H has {h.shape[1]} columns, the dictionary has {self.N} exemplars")
             ldH = h.stride(0)
             if h.stride(1) != 1 or ldH % 4 or h.data_ptr() % 16 or ldH < self.N:
-                h = _pitched(h.contiguous())
+                h = _pitched(h.contiguous(), 32)
                 ldH = h.stride(0)
             T = int(h.shape[0])
             ldY = _round_up(self.F, 4)
@@ -253,7 +253,7 @@ class ExemplarDictionary:
         L = _lib.lib()
         with torch.cuda.device(self.device):
             x = self._prep_frames(X)
-            h = _pitched(_as_device_f32(H, self.device).contiguous())
+            h = _pitched(_as_device_f32(H, self.device).contiguous(), 32)
             out = C.c_double()
             loss = _lib.LOSS_KL if beta_loss in ("kullback-leibler", 1, 1.0) else _lib.LOSS_FROBENIUS
             check(L.evc_objective(self._h, _ptr(x), x.stride(0), int(x.shape[0]), _ptr(h), h.stride(0), loss,
