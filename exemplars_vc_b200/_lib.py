@@ -76,10 +76,11 @@ def lib():
     L.evc_dict_attach_comm.argtypes = [vp, vp, ip]
     L.evc_p2p_alloc.argtypes = [vp, ip, C.c_char_p]
     L.evc_p2p_attach.argtypes = [vp, C.c_char_p, ip, ip]
+    L.evc_p2p_detach.argtypes = [vp]
     for name in ("evc_dict_create", "evc_dict_destroy", "evc_dict_info", "evc_dict_colsum", "evc_solve",
                  "evc_solve_batched", "evc_convert", "evc_reconstruct", "evc_objective", "evc_factorize_convert_host",
                  "evc_gather_stack", "evc_profile_enable", "evc_profile_read", "evc_comm_unique_id", "evc_comm_create", "evc_comm_destroy", "evc_dict_attach_comm", "evc_p2p_alloc",
-                 "evc_p2p_attach"):
+                 "evc_p2p_attach", "evc_p2p_detach"):
         getattr(L, name).restype = ip
     _lib = L
     return L

@@ -12,9 +12,13 @@ Module-level knobs replace what the reference reads from ``config/config`` at im
 
     use_stft        -- [VAR] use_stft (config/config:12); 1 = |real(stft)| branch, 0 = WORLD sp/ap/f0
     beta_override   -- the reference BODY overwrites its beta_loss argument with "frobenius"
-                       (04_align_n_nmf.py:210).  None (default) honours the argument, so the
-                       signature's default "kullback-leibler" is what runs (the north-star path);
-                       set to "frobenius" to reproduce the script literally.
+                       (04_align_n_nmf.py:210), so the script as committed runs Frobenius updates whatever
+                       the caller passes.  None (default) honours the argument instead, i.e. the signature's
+                       default "kullback-leibler" runs (the KL path this package is built around); that is a
+                       DIFFERENT result from the committed script, so the first such call warns.  Set
+                       beta_override = "frobenius" (or EVC_SCRIPT_LITERAL=1 in the environment) to reproduce
+                       the script literally (tests/test_parity_round2_gpu.py checks that path against a
+                       golden from the reference's own call).
     mode            -- arithmetic of the contractions ("3xtf32" fp32-accurate | "tf32" | "bf16" | "fp32")
     cache_dir       -- None (default): never reuse a stale H.  The reference's pickle cache
                        (04_align_n_nmf.py:251-255, keyed by feature type and file count only) is unsafe.
@@ -25,6 +29,7 @@ import hashlib
 import logging
 import os
 import pickle
+import warnings
 
 import numpy as np
 
@@ -32,13 +37,14 @@ from .dictionary import ExemplarDictionary
 from .nmf import non_negative_factorization
 
 use_stft = 1
-beta_override = None
+beta_override = "frobenius" if os.environ.get("EVC_SCRIPT_LITERAL") == "1" else None
 mode = "3xtf32"
 cache_dir = None
 max_iter = 150          # 04_align_n_nmf.py:213
 
 # The F = 1 f0 track (04_align_n_nmf.py:288) has no use for tensor cores: route it to the FFMA kernels.
 _SMALL_F = 8
+_warned_beta = False
 
 
 def _mode_for(F: int) -> str:
@@ -52,8 +58,15 @@ def _factorize(X, W, beta_loss="kullback-leibler", tol=1e-4):
     :param W: exemplar dictionary, (N, F)
     :return: H (N, T): the transposed activations, as 04_align_n_nmf.py:215 returns ``_W.T``
     """
+    global _warned_beta
     if beta_override is not None:
         beta_loss = beta_override
+    elif beta_loss != "frobenius" and not _warned_beta:
+        _warned_beta = True
+        warnings.warn("exemplars_vc_b200.align_n_nmf._factorize runs beta_loss=%r as passed; the reference script "
+                      "overwrites it with 'frobenius' (04_align_n_nmf.py:210). Set align_n_nmf.beta_override = "
+                      "'frobenius' (or EVC_SCRIPT_LITERAL=1) for the script-literal result." % (beta_loss,),
+                      stacklevel=2)
     X = np.asarray(X)
     W = np.asarray(W)
     _W, _H, n_iter = non_negative_factorization(

@@ -12,6 +12,7 @@ iteration budget.  No residual is produced and ``convert`` takes two arguments, 
 from __future__ import annotations
 
 import logging
+import warnings
 
 import numpy as np
 
@@ -22,9 +23,17 @@ use_stft = 0
 beta_override = None
 mode = "3xtf32"
 max_iter = 200          # 04_align_n_nmf_pytorch.py:208
+_warned_solver = False
 
 
 def _factorize(X, W, beta_loss="kullback-leibler", tol=1e-4):
+    global _warned_solver
+    if not _warned_solver:
+        _warned_solver = True
+        warnings.warn("exemplars_vc_b200.align_n_nmf_pytorch runs multiplicative updates (solver='mu'); the reference "
+                      "variant asks scikit-learn for solver='cd' with beta_loss='frobenius' "
+                      "(04_align_n_nmf_pytorch.py:205-208), a different algorithm with a different fixed point.",
+                      stacklevel=2)
     if beta_override is not None:
         beta_loss = beta_override
     X = np.asarray(X)

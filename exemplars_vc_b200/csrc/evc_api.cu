@@ -99,7 +99,7 @@ int contract_wh(evc_dict* d, const float* H, int ldH, int T, float* WH, int ldWH
     EVC_TRY(tc::contract_wh(d->tc_ops, d->mode, H, ldH, T, local_out, ldWH, target, &d->tcws, s, ra));
   }
   if (sharded) {
-    ProfScope ps(3, s);  // exemplar sharding: the per-iteration exchange of the partial A*H
+    ProfScope ps(4, s);  // exemplar sharding: the per-iteration exchange of the partial A*H
     if (use_p2p) EVC_TRY(p2p::all_reduce(&d->p2p, (size_t)T * ldWH, s));
     else EVC_TRY(nccl::all_reduce_sum(d->comm->comm, WH, (size_t)T * ldWH, s));
   }
@@ -164,6 +164,7 @@ int objective_segments(evc_dict* d, const float* X, int ldX, int T, const float*
   }
   EVC_CUDA(cudaMemcpyAsync(d->host_rows, d->rowd.p, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s));
   EVC_CUDA(cudaStreamSynchronize(s));
+  EVC_TRY(p2p::poll_error(&d->p2p));  // a peer that never arrived (exemplar sharding) is an error, not a hang
   const int nseg = (int)seg.size() - 1;
   err.assign(nseg, 0.0);
   for (int u = 0; u < nseg; ++u) {
@@ -234,6 +235,10 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
   std::vector<char> active(nseg, 1);
   int n_active = nseg;
   bool any_frozen = false;
+  // an utterance without frames has nothing to solve: converged before the first iteration (its err0 = 0 would make
+  // the stop test NaN and keep the loop alive until max_iter)
+  for (int u = 0; u < nseg; ++u)
+    if (seg[u + 1] == seg[u]) { active[u] = 0; conv[u] = 1; n_iter[u] = 0; --n_active; }
 
   float* num0 = d->num0.as<float>();
   if (loss == EVC_LOSS_FROBENIUS) EVC_TRY(frob_numerator(d, X, ldX, T, num0, ldH, s));
@@ -451,6 +456,7 @@ int evc_reconstruct(evc_dict_t d, const float* H, int ldH, int T, float* WH, int
 int evc_objective(evc_dict_t d, const float* X, int ldX, int T, const float* H, int ldH, int loss, float epsilon,
                   double* out, void* stream) {
   if (!d || !X || !H || !out || T < 1) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: bad argument");
+  if (ldX < d->F || ldH < d->N) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: ldX < F or ldH < N");
   if (loss != EVC_LOSS_KL && loss != EVC_LOSS_FROBENIUS) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: bad loss");
   cudaStream_t s = (cudaStream_t)stream;
   g_prof = &d->prof;
@@ -535,6 +541,12 @@ int evc_p2p_attach(evc_dict_t d, const char* handles, int rank, int world) {
   if (!d->comm || d->comm->world != world || d->comm->rank != rank)
     return fail(EVC_ERR_INVALID_ARGUMENT, "evc_p2p_attach: call evc_dict_attach_comm with the same rank/world first");
   return p2p::attach(&d->p2p, handles, rank, world);
+}
+
+int evc_p2p_detach(evc_dict_t d) {
+  if (!d) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_p2p_detach: null handle");
+  p2p::detach(&d->p2p);
+  return EVC_OK;
 }
 
 int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int* idx, const int* lo, const int* hi,

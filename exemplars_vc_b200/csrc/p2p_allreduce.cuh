@@ -10,6 +10,8 @@
 // The message is small (T x F fp32, 1-4 MB): two flag round trips + ~(world-1)/world of the message over NVLink.
 #pragma once
 #include "evc_common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace evc {
 namespace p2p {
@@ -24,7 +26,8 @@ struct Args {
   int rank, world;
   size_t n4;  // float4 elements in the message
   unsigned int epoch;
-  unsigned int* block_counter;
+  unsigned int* block_counter;  // local words: [0] block counter, [1] / [2] go-words, [3] error (1 + rank waited for)
+  long long timeout_cycles;     // a peer that does not show up within this many SM cycles is reported, not trapped on
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -42,28 +45,29 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 }
 // Poll a flag written by a peer over NVLink.  Only a handful of threads per GPU do this (with back-off): heavy
 // system-scope polling from every block slowed the peers' remote flag writes down by hundreds of microseconds.
-__device__ __forceinline__ void wait_flags(const unsigned int* flags, int idx, unsigned int epoch, const char* what) {
+// A peer that never arrives (it raised, its host stalled) must not take the CUDA context down: after the time-out the
+// wait gives up, records which rank it waited for in the error word and lets the kernel finish (with a meaningless
+// sum); the host reads the word at its next synchronisation point and returns EVC_ERR_COMM.
+__device__ __forceinline__ void wait_flags(const unsigned int* flags, int idx, unsigned int epoch, long long timeout,
+                                           unsigned int* err) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flags + idx) - epoch) < 0) {
     __nanosleep(64);
-    if (clock64() - t0 > 8000000000ll) {
-      printf("evc: p2p all-reduce timed out waiting for rank %d (%s, epoch %u)\n", idx, what, epoch);
-      __trap();
+    if (clock64() - t0 > timeout) {
+      atomicExch(err, 1u + (unsigned int)idx);
+      return;
     }
   }
 }
 // Local (same GPU) go-word: one block polls the peers, the others wait here.
+// (the launch is cooperative, so the polling block is resident and always sets the word -- at the latest when its own
+// wait times out)
 __device__ __forceinline__ void wait_local(const unsigned int* word, unsigned int epoch) {
   unsigned int v;
-  const long long t0 = clock64();
   do {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
     if ((int)(v - epoch) >= 0) break;
     __nanosleep(32);
-    if (clock64() - t0 > 8000000000ll) {
-      printf("evc: p2p all-reduce timed out on the local go-word (epoch %u)\n", epoch);
-      __trap();
-    }
   } while (true);
 }
 __device__ __forceinline__ void set_local(unsigned int* word, unsigned int epoch) {
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const Args a) {
     if (threadIdx.x < a.world) {
       __threadfence_system();  // the partial (written by the previous kernel in the stream) before the flag
       st_release_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
-      wait_flags(my_flags, threadIdx.x, a.epoch, "partials");
+      wait_flags(my_flags, threadIdx.x, a.epoch, a.timeout_cycles, words + 3);
     }
     __syncthreads();
     if (threadIdx.x == 0) set_local(words + 1, a.epoch);
@@ -129,7 +133,7 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const Args a) {
     if (threadIdx.x < a.world) {
       __threadfence_system();
       st_release_sys(a.flags[threadIdx.x] + 64 + a.rank, a.epoch);
-      wait_flags(my_flags + 64, threadIdx.x, a.epoch, "slices");
+      wait_flags(my_flags + 64, threadIdx.x, a.epoch, a.timeout_cycles, words + 3);
     }
     __syncthreads();
     if (threadIdx.x == 0) set_local(words + 2, a.epoch);
@@ -189,6 +193,25 @@ inline int attach(State* st, const char* handles, int rank, int world) {
   return EVC_OK;
 }
 
+// Unmap the peers' buffers and go back to NCCL (the local buffer stays allocated): used when not every rank could attach.
+inline void detach(State* st) {
+  for (int r = 0; r < st->world; ++r)
+    if (r != st->rank && st->peer[r]) { cudaIpcCloseMemHandle(st->peer[r]); st->peer[r] = nullptr; }
+  st->attached = false;
+}
+
+// Host side of the device time-out: call after the stream has been synchronised.
+inline int poll_error(State* st) {
+  if (!st->attached || !st->block_counter) return EVC_OK;
+  unsigned int e = 0;
+  EVC_CUDA(cudaMemcpy(&e, st->block_counter + 3, sizeof(e), cudaMemcpyDeviceToHost));
+  if (e) {
+    cudaMemset(st->block_counter + 3, 0, sizeof(e));
+    return fail(EVC_ERR_COMM, "peer-memory all-reduce: rank %u did not arrive within the time-out (EVC_P2P_TIMEOUT_S)", e - 1);
+  }
+  return EVC_OK;
+}
+
 inline void release(State* st) {
   for (int r = 0; r < st->world; ++r)
     if (r != st->rank && st->peer[r]) cudaIpcCloseMemHandle(st->peer[r]);
@@ -206,11 +229,21 @@ inline int all_reduce(State* st, size_t count, cudaStream_t s) {
     a.flags[r] = reinterpret_cast<unsigned int*>(st->peer[r]);
   }
   a.rank = st->rank; a.world = st->world; a.n4 = count / 4; a.epoch = ++st->epoch; a.block_counter = st->block_counter;
+  static const double timeout_s = getenv("EVC_P2P_TIMEOUT_S") ? atof(getenv("EVC_P2P_TIMEOUT_S")) : 60.0;
+  a.timeout_cycles = (long long)(timeout_s * 2.0e9);
   const size_t per_rank = (a.n4 + st->world - 1) / st->world;
   int blocks = (int)((per_rank + 255) / 256);
   blocks = (blocks + 1) / 2;  // two elements per thread
-  blocks = blocks < 1 ? 1 : (blocks > 120 ? 120 : blocks);
-  allreduce_kernel<<<blocks, 256, 0, s>>>(a);
+  // the blocks wait on one another (go-words): a cooperative launch guarantees they are all resident, and the grid
+  // is bounded by what the device can hold at once
+  int dev = 0, sms = 0, per_sm = 0;
+  EVC_CUDA(cudaGetDevice(&dev));
+  EVC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  EVC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, allreduce_kernel, 256, 0));
+  const int cap = std::max(1, std::min(120, sms * std::max(per_sm, 1)));
+  blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+  void* params[] = {&a};
+  EVC_CUDA(cudaLaunchCooperativeKernel((void*)allreduce_kernel, dim3(blocks), dim3(256), params, 0, s));
   EVC_LAUNCH_CHECK();
   return EVC_OK;
 }

@@ -208,6 +208,15 @@ struct TileCfg {
   static_assert(!kSplitN || (kNRows * 4) % (kEpiWarps * 32) == 0, "every split thread gets whole units");
 };
 
+// a / d with the reciprocal r = rn(1/d) of the (per-exemplar, constant) denominator at hand: q0 = a*r corrected by
+// one FMA residual step, the fast path of an IEEE division -- the correctly rounded quotient whenever it is a
+// normal number (sklearn does `numerator /= denominator; W *= numerator`, _nmf.py:617-624).
+__device__ __forceinline__ float quotient(float a, float d, float r) {
+  const float q0 = a * r;
+  const float q = fmaf(fmaf(-q0, d, a), r, q0);
+  return (q == q) ? q : q0;  // a*r overflowed or a is inf: keep the uncorrected value instead of inf - inf
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -492,6 +501,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         const int m = m_group * Cfg::kRowsPerSub + (int)rank * 128 + quarter * 32 + lane;
         float den = ((m < p.M_total && !kFro) ? p.colsum[m] : 1.f) + p.lam;
         if (den == 0.f) den = p.eps;
+        const float inv_den = __frcp_rn(den);
         // this lane's entries of the leftover dictionary rows (n_left <= 8)
         float la[8];
 #pragma unroll
@@ -524,13 +534,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
               }
             }
           } else if (p.row_active == nullptr) {
-            // one IEEE division then a multiply, as sklearn does (numerator /= denominator; W *= numerator)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = h[j] * __fdiv_rn(__uint_as_float(v[j]), den);
+            for (int j = 0; j < 32; ++j) h[j] = h[j] * quotient(__uint_as_float(v[j]), den, inv_den);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (tbm + j < p.T && p.row_active[tbm + j]) h[j] = h[j] * __fdiv_rn(__uint_as_float(v[j]), den);
+              if (tbm + j < p.T && p.row_active[tbm + j]) h[j] = h[j] * quotient(__uint_as_float(v[j]), den, inv_den);
           }
           if (kBf16 && p.out16 != nullptr && m < p.M_total) {
             // bf16 shadow of the updated activations: 64 contiguous bytes per warp per frame, straight from registers
@@ -660,18 +669,18 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
     if (f0 + 4 <= F_main && (f0 >= f_last || f0 + 4 <= f_last)) {
       const int n = (f0 >= f_last) ? S_last : S;  // columns of the last row group have their own split count
       const float* p0 = P + (size_t)t * ldp + f0;
-      // batches of 6 independent 16-byte loads in flight, summed in split order (deterministic)
-      int k = 0;
-      for (; k + 6 <= n; k += 6) {
-        float4 v[6];
+      // every split's 16-byte load in flight at once (batches of kRB, predicated), summed in split order: one
+      // memory round trip per batch, deterministic result
+      constexpr int kRB = 20;
+      for (int k = 0; k < n; k += kRB) {
+        float4 v[kRB];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) v[q] = *reinterpret_cast<const float4*>(p0 + (size_t)(k + q) * T * ldp);
+        for (int q = 0; q < kRB; ++q)
+          v[q] = (k + q < n) ? __ldcs(reinterpret_cast<const float4*>(p0 + (size_t)(k + q) * T * ldp))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) { s[0] += v[q].x; s[1] += v[q].y; s[2] += v[q].z; s[3] += v[q].w; }
-      }
-      for (; k < n; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(p0 + (size_t)k * T * ldp);
-        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        for (int q = 0; q < kRB; ++q)
+          if (k + q < n) { s[0] += v[q].x; s[1] += v[q].y; s[2] += v[q].z; s[3] += v[q].w; }
       }
       have[0] = have[1] = have[2] = have[3] = true;
     } else {

@@ -27,6 +27,7 @@ class Activation:
     converged: bool
     objective: float
     objective_at_init: float
+    H_stacked: Optional[torch.Tensor] = None   # solve_batched: the (T_total, N) tensor every utterance's H is a row view of
 
 
 def _round_up(a: int, b: int) -> int:
@@ -159,6 +160,10 @@ class ExemplarDictionary:
         with torch.cuda.device(self.device):
             check(_lib.lib().evc_p2p_attach(self._h, blob, rank, world))
 
+    def p2p_detach(self):
+        """Back to ncclAllReduce (every rank must use the same exchange; see sharding.make_exemplar_sharded)."""
+        check(_lib.lib().evc_p2p_detach(self._h))
+
     # -- the hot path ---------------------------------------------------------------------------------
     def _params(self, beta_loss, tol, max_iter, lam, lambda_step, init_given, check_every, epsilon) -> SolveParams:
         p = SolveParams()
@@ -219,6 +224,8 @@ class ExemplarDictionary:
         for u in range(n_utt):
             out.append(Activation(H[offs[u]:offs[u + 1]], res[u].n_iter, bool(res[u].converged),
                                   res[u].objective, res[u].objective_at_init))
+        for a in out:
+            a.H_stacked = H
         if t_offsets is None:
             out[0].H = H
         return out
@@ -266,11 +273,11 @@ class ExemplarDictionary:
 
     def profile_read(self):
         """{class: (milliseconds, launches)} since the last read; classes as in include/evc.h."""
-        ms = (C.c_double * 4)()
-        n = (C.c_int * 4)()
+        names = ("contraction1", "reduce_ratio", "contraction2_update", "objective_init", "exchange")
+        ms = (C.c_double * len(names))()
+        n = (C.c_int * len(names))()
         check(_lib.lib().evc_profile_read(self._h, ms, n))
-        names = ("contraction1", "reduce_ratio", "contraction2_update", "objective_init")
-        return {names[i]: (ms[i], n[i]) for i in range(4)}
+        return {names[i]: (ms[i], n[i]) for i in range(len(names))}
 
     # -- host staging --------------------------------------------------------------------------------
     def to_host(self, t: torch.Tensor, key: Optional[str] = None) -> np.ndarray:

@@ -9,6 +9,12 @@ Same name, argument meaning, return triple and error behaviour as
 configuration on the path -- fixed dictionary (``update_H=False``, ``init='custom'``), multiplicative
 updates (``solver='mu'``), beta in {KL, Frobenius}.  The arithmetic runs on the GPU through
 libevc_b200 (no CPU path); numpy in, numpy out, output dtype = dtype of X.
+
+Precision note: float64 inputs (the dtype of the reference's WORLD branch, pyworld returns float64) are
+COMPUTED in float32 on the device (fp32-accurate split products, fp32 accumulation and update) and the
+result is cast back to float64 -- inside the 1e-3 / 1e-4 tolerances the parity tests assert against the
+float64 reference, but not a float64 computation: quantities that depend on the sign of tiny differences
+(e.g. which entries of ``log(H^T A - X)`` at 04_align_n_nmf.py:292 come out NaN) can differ.
 """
 from __future__ import annotations
 
@@ -74,6 +80,13 @@ def non_negative_factorization(X, W=None, H=None, n_components="auto", *, init=N
     if X_in.dtype not in (np.float64, np.float32):
         X_in = X_in.astype(np.float64)          # sklearn check_array(dtype=[float64, float32])
     H_arr = np.asarray(H)
+    # sklearn check_array(force_all_finite=True) runs before the sign check (NaN < 0 is False, so a NaN would
+    # otherwise slip through): same exception type and wording
+    for name, arr in (("X", X_in), ("H", H_arr)):
+        if arr.dtype.kind == "f" and arr.size and not np.isfinite(arr).all():
+            if np.isnan(arr).any():
+                raise ValueError("Input %s contains NaN." % name)
+            raise ValueError("Input %s contains infinity or a value too large for %r." % (name, arr.dtype))
     if X_in.size and X_in.min() < 0:
         raise ValueError("Negative values in data passed to NMF (input X)")
     _check_dictionary_dtype(X_in, H_arr)

@@ -99,9 +99,13 @@ def make_exemplar_sharded(A_rows: Callable[[int, int], np.ndarray], B_rows: Opti
 
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    n0, n1 = exemplar_range(N, rank, world)
-    if n1 <= n0:
-        raise ValueError(f"rank {rank} owns no exemplars (N={N}, world={world})")
+    # every rank can compute every rank's range: an empty shard makes ALL ranks raise, before any collective is
+    # entered (one rank raising alone would leave the others hanging in the broadcast below)
+    ranges = [exemplar_range(N, r, world) for r in range(world)]
+    empty = [r for r, (a, b) in enumerate(ranges) if b <= a]
+    if empty:
+        raise ValueError(f"ranks {empty} would own no exemplars (N={N}, world={world}): use fewer ranks")
+    n0, n1 = ranges[rank]
     d = ExemplarDictionary(A_rows(n0, n1), B_rows(n0, n1) if B_rows is not None else None, mode=mode)
 
     def make_id() -> bytes:
@@ -134,9 +138,12 @@ def make_exemplar_sharded(A_rows: Callable[[int, int], np.ndarray], B_rows: Opti
         dist.all_gather_object(oks, ok, group=group)
         if all(oks):
             d.all_reduce = "p2p"
-        elif ok:
-            raise RuntimeError("peer-memory all-reduce attached on this rank but not on all ranks: " + repr(oks))
-        elif err and rank == 0:
-            import warnings
-            warnings.warn("peer-memory all-reduce unavailable, using NCCL: " + err)
+        else:
+            # not every rank could map its peers: ALL ranks use NCCL (a rank that did attach lets go again)
+            if ok:
+                d.p2p_detach()
+            if rank == 0:
+                import warnings
+                warnings.warn("peer-memory all-reduce unavailable on ranks %s, using NCCL on all ranks%s"
+                              % ([r for r, o_ in enumerate(oks) if not o_], (": " + err) if err else ""))
     return d

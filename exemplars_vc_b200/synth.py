@@ -22,6 +22,11 @@ class Workload:
     iterations: int
     n_utt: int = 1
     description: str = ""
+    tol: float = 0.0          # 0: run all `iterations` (the bench configs); > 0: the reference's stop rule
+
+
+def utterance_lengths(seed: int, n_utt: int, lo: int = 400, hi: int = 600):
+    return np.random.default_rng(seed + 4).integers(lo, hi + 1, size=n_utt).astype(np.int64)
 
 
 CONFIGS = {
@@ -29,7 +34,8 @@ CONFIGS = {
     "single_utterance_20k": Workload("single_utterance_20k", 513, 20000, 1000, 500, 1,
                                      "synthetic single utterance F=513 N=20000 T=1000, 500 KL-MU iterations"),
     # configs[2]: 256 utterances, T ~ U[400,600]
-    "batch_256utt_20k": Workload("batch_256utt_20k", 513, 20000, 0, 500, 256,
+    "batch_256utt_20k": Workload("batch_256utt_20k", 513, 20000, int(utterance_lengths(BASE_SEED + 2, 256).sum()),
+                                 500, 256,
                                  "256 synthetic utterances (T~U[400,600]) against one shared 513x20k dictionary pair"),
     # configs[3]
     "large_dictionary_200k": Workload("large_dictionary_200k", 513, 200000, 2000, 500, 1,
@@ -37,6 +43,11 @@ CONFIGS = {
     # configs[4]
     "context_stacked_50k": Workload("context_stacked_50k", 2565, 50000, 1000, 500, 1,
                                     "+-2-frame stacked exemplars F=2565 N=50000 T=1000"),
+    # configs[0] at the size the reference's own logs show (20 files -> N ~ 20.7k exemplars,
+    # utterance 100162 -> T = 688 frames) with the reference's settings: max_iter = 150, tol = 1e-4
+    # (04_align_n_nmf.py:194, 213), called through the script-level drop-in with the dictionary upload included
+    "reference_default": Workload("reference_default", 513, 20727, 688, 150, 1,
+                                  "the reference's real call: T=688, N=20727, max_iter=150, tol=1e-4", 1e-4),
 }
 
 
@@ -65,7 +76,3 @@ def frames(seed: int, A: np.ndarray, T: int, dtype=np.float32, exact: bool = Fal
         X = np.einsum("tk,tkf->tf", w, A[idx].astype(np.float64))
     X = X + 0.01 * np.random.default_rng(seed + 3).random((T, F))
     return X.astype(dtype)
-
-
-def utterance_lengths(seed: int, n_utt: int, lo: int = 400, hi: int = 600):
-    return np.random.default_rng(seed + 4).integers(lo, hi + 1, size=n_utt).astype(np.int64)

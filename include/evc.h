@@ -178,6 +178,10 @@ int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int
  */
 int evc_p2p_alloc(evc_dict_t d, int max_frames, char handle_out[64]);
 int evc_p2p_attach(evc_dict_t d, const char* handles, int rank, int world);
+/* Unmap the peers' buffers again: the handle goes back to the NCCL all-reduce.  Used when not EVERY rank could attach
+ * (all ranks must use the same exchange).  A peer that does not arrive within EVC_P2P_TIMEOUT_S seconds (default 60)
+ * makes the next synchronising call return EVC_ERR_COMM instead of hanging or trapping. */
+int evc_p2p_detach(evc_dict_t d);
 
 /* Diagnostics: host milliseconds the last evc_solve* on this thread spent ENQUEUEING its iteration loop (if this
  * approaches the device time of the loop, the GPU is waiting for the host). */
@@ -197,9 +201,10 @@ int evc_mma_passes_per_product(int mode);
  * bracketed by CUDA events on the caller's stream; evc_profile_read synchronises, sums the elapsed times per
  * class, returns them and clears the log.  Classes: 0 = contraction 1 (A*H, B*H: tensor/FFMA GEMM),
  * 1 = split-K reduction + ratio (memory-bound), 2 = contraction 2 with the fused multiplicative update,
- * 3 = objective / init helpers.  ms[4] and launches[4] are host arrays.
+ * 3 = objective / init helpers, 4 = the per-iteration exchange of the partial A*H when the exemplar dimension
+ * is sharded.  ms[EVC_PROFILE_CLASSES] and launches[EVC_PROFILE_CLASSES] are host arrays.
  */
-#define EVC_PROFILE_CLASSES 4
+#define EVC_PROFILE_CLASSES 5
 int evc_profile_enable(evc_dict_t d, int on);
 int evc_profile_read(evc_dict_t d, double* ms, int* launches);
 

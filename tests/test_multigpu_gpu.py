@@ -69,3 +69,21 @@ def test_sharded_paths_two_gpus(mode):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, 29600 + os.getpid() % 1000, mode), nprocs=2, join=True)
+
+
+def test_two_devices_in_one_process():
+    """the > 48 KB dynamic shared-memory opt-in and the SM count are per-device state; a second GPU used
+    from the same process must launch the tensor-core kernels too."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    from exemplars_vc_b200 import ExemplarDictionary
+    from oracle import nmf_oracle as o
+    X, A, B = o.gen(17, 257, 640, 24)
+    W_ref, n_ref, obj = o.kl_mu(X, A, tol=1e-4, max_iter=30)
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        with torch.cuda.device(dev):
+            with ExemplarDictionary(A, B, mode="3xtf32", device=dev) as d:
+                act = d.solve(X, tol=1e-4, max_iter=30)
+                H = d.to_host(act.H).astype(np.float64)
+        assert act.n_iter == n_ref and np.linalg.norm(H - W_ref) / np.linalg.norm(W_ref) < 1e-3, dev
