@@ -33,7 +33,7 @@ import warnings
 
 import numpy as np
 
-from .dictionary import ExemplarDictionary
+from .dictionary import dictionary_cache
 from .nmf import non_negative_factorization
 
 use_stft = 1
@@ -71,8 +71,29 @@ def _factorize(X, W, beta_loss="kullback-leibler", tol=1e-4):
     W = np.asarray(W)
     _W, _H, n_iter = non_negative_factorization(
         X=X, H=W, init="custom", update_H=False, n_components=W.shape[0], beta_loss=beta_loss, solver="mu",
-        tol=tol, max_iter=max_iter, verbose=0, mode=_mode_for(W.shape[1]))
+        tol=tol, max_iter=max_iter, verbose=0, mode=_mode_for(W.shape[1]), _device_result=_keep)
     return _W.T
+
+
+_keep = None    # set by _factorize_with_residual: receives the device-resident dictionary + activations of the call
+
+
+def _factorize_with_residual(X, W):
+    """H (N,T) as `_factorize`, plus the WORLD-branch residual log(H^T W - X) (04_align_n_nmf.py:292-294) formed on the
+    device from the activations that are still resident there (no second upload, no host matmul)."""
+    global _keep
+    _keep = {}
+    try:
+        H = _factorize(X=X, W=W)
+        d, act = _keep.get("dictionary"), _keep.get("activation")
+    finally:
+        _keep = None
+    if d is None:          # dictionary cache switched off: the handle is gone, go through a fresh one
+        d = dictionary_cache.get(np.asarray(W), None, _mode_for(np.asarray(W).shape[1]))
+        R = d.to_host(d.residual(X, np.ascontiguousarray(H.T)))
+    else:
+        R = d.to_host(d.residual(X, act.H))
+    return H, R.astype(np.result_type(H.dtype, np.asarray(X).dtype), copy=False)
 
 
 def _stack(feats, key, absolute=False):
@@ -112,13 +133,11 @@ def factorize(tobe_converted, src_feat):
         if path and os.path.isfile(path):
             with open(path, "rb") as f:
                 return pickle.load(f)
-        H = {"H_sp": _factorize(X=conv_sp, W=A_sp), "H_ap": _factorize(X=conv_ap, W=A_ap),
-             "H_f0": _factorize(X=conv_f0, W=A_f0)}
-        # residual compensation, 04_align_n_nmf.py:292-294 (NaN wherever H^T A <= X, by construction)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            R = {"r_sp": np.log(np.matmul(H["H_sp"].T, A_sp) - conv_sp),
-                 "r_ap": np.log(np.matmul(H["H_ap"].T, A_ap) - conv_ap),
-                 "r_f0": np.log(np.matmul(H["H_f0"].T, A_f0) - conv_f0)}
+        # activations + residual compensation log(H^T A - X), 04_align_n_nmf.py:284-294 (NaN wherever H^T A < X, by
+        # construction); the product and the logarithm run on the device, next to the activations
+        H, R = {}, {}
+        for k, X_k, A_k in (("sp", conv_sp, A_sp), ("ap", conv_ap, A_ap), ("f0", conv_f0, A_f0)):
+            H["H_" + k], R["r_" + k] = _factorize_with_residual(X_k, A_k)
         if path:
             os.makedirs(cache_dir, exist_ok=True)
             with open(path, "wb") as f:
@@ -138,12 +157,14 @@ def factorize(tobe_converted, src_feat):
     return H, None
 
 
-def _product(H_nt, B):
-    """np.matmul(H.T, B) on the GPU (04_align_n_nmf.py:371-373, 391)."""
+def _product(H_nt, B, residual=None):
+    """np.matmul(H.T, B) on the GPU (04_align_n_nmf.py:391); with `residual` the whole WORLD-branch expression
+    exp(log(H.T @ B) + log(residual)) of 04_align_n_nmf.py:371-373 in one pass (NaN -> 0 rule of :363-365 included).
+    The target dictionary stays resident between calls (dictionary.DictionaryCache)."""
     H_nt = np.asarray(H_nt)
     B = np.asarray(B)
-    with ExemplarDictionary(B, B, mode=_mode_for(B.shape[1])) as d:
-        y = d.to_host(d.convert(np.ascontiguousarray(H_nt.T)))
+    d = dictionary_cache.get(B, B, _mode_for(B.shape[1]))
+    y = d.to_host(d.convert(np.ascontiguousarray(H_nt.T), residual=residual))
     return y.astype(np.result_type(H_nt.dtype, B.dtype), copy=False)
 
 
@@ -153,11 +174,11 @@ def convert(H, tar_feat, residual):
     if not use_stft:
         B_sp, B_ap, B_f0 = _stack(tar_feat, "sp"), _stack(tar_feat, "ap"), _stack(tar_feat, "f0")
         for k in ("r_sp", "r_ap", "r_f0"):
-            residual[k][np.isnan(residual[k])] = 0          # :363-365
-        with np.errstate(invalid="ignore", divide="ignore"):
-            converted_sp = np.exp(np.log(_product(H["H_sp"], B_sp)) + np.log(residual["r_sp"]))
-            converted_ap = np.exp(np.log(_product(H["H_ap"], B_ap)) + np.log(residual["r_ap"]))
-            converted_f0 = np.exp(np.log(_product(H["H_f0"], B_f0)) + np.log(residual["r_f0"]))
+            residual[k][np.isnan(residual[k])] = 0          # :363-365 (in place, like the reference)
+        # exp(log(H^T B) + log(r)), :371-373, as the epilogue of the conversion product on the device
+        converted_sp = _product(H["H_sp"], B_sp, residual["r_sp"])
+        converted_ap = _product(H["H_ap"], B_ap, residual["r_ap"])
+        converted_f0 = _product(H["H_f0"], B_f0, residual["r_f0"])
         return {"sp": converted_sp, "ap": converted_ap, "f0": np.squeeze(converted_f0)}
     B_stft = _stack(tar_feat, "real", absolute=True)
     return _product(H["H_stft"], B_stft)                  # :391

@@ -11,7 +11,9 @@
 #include "tc_kernels.cuh"
 #include "nccl_shim.cuh"
 #include "p2p_allreduce.cuh"
+#include "audio_kernels.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <new>
@@ -38,6 +40,7 @@ struct evc_dict {
   p2p::State p2p;            // ... by our own kernel over NVLink peer memory when attached (else NCCL)
   // per-solve workspace, grow-only
   DevBuf WH, R, rowd, w0, active, num0, tcws;
+  DevBuf hostX, hostH, hostY;   // device staging of evc_factorize_convert_host (grow-only: no cudaMalloc per call)
   double* host_rows = nullptr;  // pinned mirror of rowd
   size_t host_rows_cap = 0;
   float* host_w0 = nullptr;     // pinned
@@ -220,8 +223,7 @@ int solve_impl(evc_dict* d, const float* X, int ldX, const int* t_offsets, int n
       for (int t = seg[u]; t < seg[u + 1]; ++t) d->host_w0[t] = w0;
     }
     EVC_CUDA(cudaMemcpyAsync(d->w0.p, d->host_w0, (size_t)T * sizeof(float), cudaMemcpyHostToDevice, s));
-    dim3 g(T, ceil_div(d->N, 256));
-    simt::fill_rows_kernel<<<g, 256, 0, s>>>(H, ldH, T, d->N, d->w0.as<float>());
+    simt::fill_rows_kernel<<<T, 256, 0, s>>>(H, ldH, T, d->N, d->w0.as<float>());
     EVC_LAUNCH_CHECK();
   } else if (p->init != EVC_INIT_GIVEN) {
     return fail(EVC_ERR_INVALID_ARGUMENT, "evc_solve: init must be EVC_INIT_SKLEARN or EVC_INIT_GIVEN");
@@ -333,6 +335,7 @@ int evc_dict_destroy(evc_dict_t d) {
   d->tc_ops.release();
   d->WH.release(); d->R.release(); d->rowd.release(); d->w0.release(); d->active.release();
   d->num0.release(); d->tcws.release(); d->prof.release(); p2p::release(&d->p2p);
+  d->hostX.release(); d->hostH.release(); d->hostY.release();
   if (g_prof == &d->prof) g_prof = nullptr;
   if (d->host_rows) cudaFreeHost(d->host_rows);
   if (d->host_w0) cudaFreeHost(d->host_w0);
@@ -453,6 +456,97 @@ int evc_reconstruct(evc_dict_t d, const float* H, int ldH, int T, float* WH, int
   return product_impl(d, H, ldH, T, WH, ldWH, false, stream, "evc_reconstruct");
 }
 
+// ---- the step right after the path: residual compensation epilogues and the Griffin-Lim vocoder ----
+
+int evc_residual(evc_dict_t d, const float* X, int ldX, int T, const float* H, int ldH, float* R, int ldR, void* stream) {
+  if (!d || !X || !H || !R || T < 0) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_residual: null argument");
+  if (ldX < d->F || ldH < d->N || ldR < d->F) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_residual: pitch smaller than the row length");
+  if (T == 0) return EVC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  g_prof = &d->prof;
+  EVC_TRY(tc::check_alignment(d->mode, H, ldH));
+  EVC_TRY(reserve_workspace(d, T, ldH, false));
+  EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
+  EVC_TRY(contract_wh(d, H, ldH, T, wh_buf(d), d->ldWH, false, s));
+  dim3 g(T, ceil_div(d->F, 128));
+  audio::residual_kernel<<<g, 128, 0, s>>>(wh_buf(d), d->ldWH, X, ldX, R, ldR, T, d->F);
+  EVC_LAUNCH_CHECK();
+  return EVC_OK;
+}
+
+int evc_convert_residual(evc_dict_t d, const float* H, int ldH, int T, const float* R, int ldR, float* Y, int ldY,
+                         void* stream) {
+  if (!d || !H || !R || !Y || T < 0) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_convert_residual: null argument");
+  if (!d->has_target) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_convert_residual: dictionary was created without a target B");
+  if (ldH < d->N || ldR < d->F || ldY < d->F)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_convert_residual: pitch smaller than the row length");
+  if (T == 0) return EVC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  g_prof = &d->prof;
+  EVC_TRY(tc::check_alignment(d->mode, H, ldH));
+  EVC_TRY(reserve_workspace(d, T, ldH, false));
+  EVC_TRY(tc::after_h_written(d->tc_ops, d->mode, H, ldH, T, &d->tcws, s));
+  EVC_TRY(contract_wh(d, H, ldH, T, wh_buf(d), d->ldWH, true, s));
+  dim3 g(T, ceil_div(d->F, 128));
+  audio::apply_residual_kernel<<<g, 128, 0, s>>>(wh_buf(d), d->ldWH, R, ldR, Y, ldY, T, d->F);
+  EVC_LAUNCH_CHECK();
+  return EVC_OK;
+}
+
+int evc_stft(const double* x, long long len, int fft_size, int hop, const double* window, double* spec, void* stream) {
+  if (!x || !window || !spec || len <= fft_size) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_stft: bad argument");
+  const int T = (int)((len - fft_size + hop - 1) / hop);  // range(0, len - fft_size, hop)
+  EVC_TRY(audio::gl_check(T, fft_size, hop));
+  return audio::gl_launch_frames(audio::GL_STFT, x, window, nullptr, 0, spec, T, fft_size, hop, nullptr, (cudaStream_t)stream);
+}
+
+int evc_istft(const double* spec, int T, int fft_size, int hop, const double* window, double* x_out, void* stream) {
+  if (!spec || !window || !x_out) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_istft: null argument");
+  EVC_TRY(audio::gl_check(T, fft_size, hop));
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long len = (long long)T * hop + fft_size;
+  double* frames = nullptr;
+  EVC_CUDA(cudaMallocAsync(&frames, (size_t)T * fft_size * sizeof(double), s));
+  int st = audio::gl_launch_frames(audio::GL_ISTFT, nullptr, window, nullptr, 0, const_cast<double*>(spec), T, fft_size, hop,
+                                   frames, s);
+  if (st == EVC_OK) {
+    audio::gl_overlap_add_kernel<<<(unsigned)((len + 255) / 256), 256, 0, s>>>(frames, T, fft_size, hop, len, x_out, nullptr, nullptr);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (cudaGetLastError() != cudaSuccess) st = fail(EVC_ERR_CUDA, "evc_istft: overlap-add launch failed");
+  }
+  cudaFreeAsync(frames, s);
+  return st;
+}
+
+int evc_griffin_lim(const float* mag, int ldm, int T, int fft_size, int hop, int iterations, const double* window,
+                    const double* x0, double* x_out, double* sq_diff, void* stream) {
+  if (!mag || !window || !x0 || !x_out || iterations < 0) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_griffin_lim: bad argument");
+  EVC_TRY(audio::gl_check(T, fft_size, hop));
+  if (ldm < fft_size / 2 + 1) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_griffin_lim: ldm < fft_size/2 + 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long len = (long long)T * hop + fft_size;
+  double *frames = nullptr, *xa = nullptr, *xb = nullptr;
+  EVC_CUDA(cudaMallocAsync(&frames, (size_t)T * fft_size * sizeof(double), s));
+  EVC_CUDA(cudaMallocAsync(&xa, (size_t)len * sizeof(double), s));
+  EVC_CUDA(cudaMallocAsync(&xb, (size_t)len * sizeof(double), s));
+  int st = [&]() -> int {
+    EVC_CUDA(cudaMemcpyAsync(xa, x0, (size_t)len * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (sq_diff && iterations > 0) EVC_CUDA(cudaMemsetAsync(sq_diff, 0, (size_t)iterations * sizeof(double), s));
+    double *cur = xa, *nxt = xb;
+    for (int it = 0; it < iterations; ++it) {
+      EVC_TRY(audio::gl_launch_frames(audio::GL_ITERATE, cur, window, mag, ldm, nullptr, T, fft_size, hop, frames, s));
+      audio::gl_overlap_add_kernel<<<(unsigned)((len + 255) / 256), 256, 0, s>>>(frames, T, fft_size, hop, len, nxt, cur,
+                                                                                sq_diff ? sq_diff + it : nullptr);
+      EVC_LAUNCH_CHECK();
+      std::swap(cur, nxt);
+    }
+    EVC_CUDA(cudaMemcpyAsync(x_out, cur, (size_t)len * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return EVC_OK;
+  }();
+  cudaFreeAsync(frames, s); cudaFreeAsync(xa, s); cudaFreeAsync(xb, s);
+  return st;
+}
+
 int evc_objective(evc_dict_t d, const float* X, int ldX, int T, const float* H, int ldH, int loss, float epsilon,
                   double* out, void* stream) {
   if (!d || !X || !H || !out || T < 1) return fail(EVC_ERR_INVALID_ARGUMENT, "evc_objective: bad argument");
@@ -480,26 +574,22 @@ int evc_factorize_convert_host(evc_dict_t d, const float* X, int ldX, int T, flo
   if (T == 0) return EVC_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int ldXd = round_up(d->F, 4), ldHd = round_up(d->N, 32), ldYd = round_up(d->F, 4);
-  float *dX = nullptr, *dH = nullptr, *dY = nullptr;
-  int st = [&]() -> int {
-    EVC_CUDA(cudaMalloc(&dX, (size_t)T * ldXd * sizeof(float)));
-    EVC_CUDA(cudaMalloc(&dH, (size_t)T * ldHd * sizeof(float)));
-    EVC_CUDA(cudaMemcpy2DAsync(dX, (size_t)ldXd * 4, X, (size_t)ldX * 4, (size_t)d->F * 4, T, cudaMemcpyHostToDevice, s));
-    if (p->init == EVC_INIT_GIVEN)
-      EVC_CUDA(cudaMemcpy2DAsync(dH, (size_t)ldHd * 4, H, (size_t)ldH * 4, (size_t)d->N * 4, T, cudaMemcpyHostToDevice, s));
-    EVC_TRY(evc_solve(d, dX, ldXd, T, dH, ldHd, p, res, s));
-    if (Y) {
-      EVC_CUDA(cudaMalloc(&dY, (size_t)T * ldYd * sizeof(float)));
-      EVC_TRY(evc_convert(d, dH, ldHd, T, dY, ldYd, s));
-      EVC_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldY * 4, dY, (size_t)ldYd * 4, (size_t)d->F * 4, T, cudaMemcpyDeviceToHost, s));
-    }
-    if (H)
-      EVC_CUDA(cudaMemcpy2DAsync(H, (size_t)ldH * 4, dH, (size_t)ldHd * 4, (size_t)d->N * 4, T, cudaMemcpyDeviceToHost, s));
-    EVC_CUDA(cudaStreamSynchronize(s));
-    return EVC_OK;
-  }();
-  cudaFree(dX); cudaFree(dH); cudaFree(dY);
-  return st;
+  EVC_TRY(d->hostX.reserve((size_t)T * ldXd * sizeof(float)));
+  EVC_TRY(d->hostH.reserve((size_t)T * ldHd * sizeof(float)));
+  if (Y) EVC_TRY(d->hostY.reserve((size_t)T * ldYd * sizeof(float)));
+  float *dX = d->hostX.as<float>(), *dH = d->hostH.as<float>(), *dY = d->hostY.as<float>();
+  EVC_CUDA(cudaMemcpy2DAsync(dX, (size_t)ldXd * 4, X, (size_t)ldX * 4, (size_t)d->F * 4, T, cudaMemcpyHostToDevice, s));
+  if (p->init == EVC_INIT_GIVEN)
+    EVC_CUDA(cudaMemcpy2DAsync(dH, (size_t)ldHd * 4, H, (size_t)ldH * 4, (size_t)d->N * 4, T, cudaMemcpyHostToDevice, s));
+  EVC_TRY(evc_solve(d, dX, ldXd, T, dH, ldHd, p, res, s));
+  if (Y) {
+    EVC_TRY(evc_convert(d, dH, ldHd, T, dY, ldYd, s));
+    EVC_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldY * 4, dY, (size_t)ldYd * 4, (size_t)d->F * 4, T, cudaMemcpyDeviceToHost, s));
+  }
+  if (H)
+    EVC_CUDA(cudaMemcpy2DAsync(H, (size_t)ldH * 4, dH, (size_t)ldHd * 4, (size_t)d->N * 4, T, cudaMemcpyDeviceToHost, s));
+  EVC_CUDA(cudaStreamSynchronize(s));
+  return EVC_OK;
 }
 
 int evc_comm_unique_id(char id_out[128]) { return nccl::unique_id(id_out); }

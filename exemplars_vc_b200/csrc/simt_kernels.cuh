@@ -166,11 +166,22 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, int N, int F
   if (__any_sync(0xffffffffu, nz) && lane == 0) atomicOr(&flags[1], 1);
 }
 
-// H[t, :] = w0[t]  (sklearn _nmf.py:1225-1226, one value per utterance)
-__global__ void fill_rows_kernel(float* __restrict__ H, int ldh, int T, int N, const float* __restrict__ w0) {
-  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+// H[t, :] = w0[t]  (sklearn _nmf.py:1225-1226, one value per utterance).  One block per frame, 16-byte stores when the
+// row is 16-byte aligned (it is for every H this library allocates): an 80 MB fill runs at HBM write speed instead of
+// being bound by the launch shape of 79 000 one-float-per-thread blocks (profiles/r1_ncu_memory_bound_summary.txt).
+__global__ void __launch_bounds__(256) fill_rows_kernel(float* __restrict__ H, int ldh, int T, int N, const float* __restrict__ w0) {
   const int t = blockIdx.x;
-  if (n < N && t < T) H[(size_t)t * ldh + n] = w0[t];
+  if (t >= T) return;
+  const float v = w0[t];
+  float* row = H + (size_t)t * ldh;
+  if ((((uintptr_t)row) & 15) == 0) {
+    const int n4 = N >> 2;
+    const float4 v4 = make_float4(v, v, v, v);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<float4*>(row)[i] = v4;
+    for (int n = (n4 << 2) + threadIdx.x; n < N; n += blockDim.x) row[n] = v;
+  } else {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) row[n] = v;
+  }
 }
 
 // R = X / max(WH, eps)   (sklearn _nmf.py:568-571); columns [F, ldr) of R are zeroed so that R can be a

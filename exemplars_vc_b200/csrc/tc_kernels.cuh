@@ -635,76 +635,89 @@ __device__ __forceinline__ void store_r(const ROut& o, int t, int f, float r) {
 }
 
 // WH[t,f] = sum_s P[s][t][f] for the tensor-core rows f < F_main (fixed order: deterministic);
-// WH[t,F_main+l] = sum_r L[l][t][r] from the fused update's per-warp partials when `left_rows` > 0 (the block
-// that owns those columns reduces the `left_rows` contiguous partials of its frame first).
+// WH[t,F_main+l] = sum_r L[l][t][r] from the fused update's per-warp partials when `left_rows` > 0.
 // With `X` != nullptr it also emits the ratio R = X / max(WH, eps) (zero pad columns) in the same pass.
+//
+// One block per (frame, 512-column chunk).  The split-K partials of the chunk -- S segments of 2 KB, megabytes apart
+// in the workspace -- are staged in shared memory by cp.async.bulk copies issued by one thread and summed from there:
+// with per-lane 16-byte loads this kernel ran at 2.0 TB/s (the SM's outstanding-miss capacity, profiles/r2c_*),
+// bulk copies are not subject to that limit.
+constexpr int kRedCols = 512, kRedMaxBatch = 32;
 __global__ void __launch_bounds__(128)
 reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
                        float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
-                       int left_ld, const float* __restrict__ X, int ldx, float eps, ROut ro) {
-  // one block per frame; a thread owns groups of 4 consecutive columns (16-byte loads of the partials)
+                       int left_ld, const float* __restrict__ X, int ldx, float eps, ROut ro, int batch) {
+  extern __shared__ __align__(128) float red_smem[];  // [batch][kRedCols] staged partials | [n_left][left_rows]
+  __shared__ __align__(8) uint64_t bar;
   __shared__ float s_left[8];
   __shared__ float s_warp[4];
+  const int t = blockIdx.x, c0 = blockIdx.y * kRedCols;
+  float* stage = red_smem;
+  float* lstage = red_smem + (size_t)batch * kRedCols;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
-  const int t = blockIdx.x;
-  if (t >= T) return;
-  if (left_rows > 0) {
-    for (int l = 0; l < n_left; ++l) {
-      const float* row = L + ((size_t)l * left_ld + t) * left_rows;
-      float a = 0.f;
-      for (int r = threadIdx.x; r < left_rows; r += blockDim.x) a += row[r];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = a;
-      __syncthreads();
-      if (threadIdx.x == 0) s_left[l] = (s_warp[0] + s_warp[1]) + (s_warp[2] + s_warp[3]);
-      __syncthreads();
+  const int pcols = max(0, min(kRedCols, min(ldp, F_main) - c0));  // tensor-core columns of this chunk (a multiple of 4)
+  const int pcols_ld = max(0, min(kRedCols, ldp - c0));             // ... including the partial buffer's pad columns
+  const int n = (c0 >= f_last) ? S_last : S;                        // the last row group has its own split count
+  const bool has_left = left_rows > 0 && F_main >= c0 && F_main < c0 + kRedCols;
+  uint32_t phase = 0;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int col = threadIdx.x * 4;  // this thread's 4 columns of the chunk
+  for (int k0 = 0; k0 < n || (k0 == 0 && has_left); k0 += batch) {
+    const int nb = max(0, min(batch, n - k0));
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (pcols_ld > 0 ? (uint32_t)nb * pcols_ld * 4u : 0u);
+      if (k0 == 0 && has_left) bytes += (uint32_t)n_left * left_rows * 4u;
+      mbar_arrive_expect_tx(smem_u32(&bar), bytes);
+      if (pcols_ld > 0)
+        for (int k = 0; k < nb; ++k)
+          bulk_load_1d(smem_u32(stage + (size_t)k * kRedCols), P + ((size_t)(k0 + k) * T + t) * ldp + c0,
+                       (uint32_t)pcols_ld * 4u, smem_u32(&bar), kEvictFirst);
+      if (k0 == 0 && has_left)
+        for (int l = 0; l < n_left; ++l)
+          bulk_load_1d(smem_u32(lstage + (size_t)l * left_rows), L + ((size_t)l * left_ld + t) * left_rows,
+                       (uint32_t)left_rows * 4u, smem_u32(&bar), kEvictFirst);
     }
+    mbar_wait(smem_u32(&bar), phase);
+    phase ^= 1u;
+    if (col < pcols)
+      for (int k = 0; k < nb; ++k) {  // split order: deterministic
+        const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)k * kRedCols + col);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    if (k0 == 0 && has_left) {
+      for (int l = 0; l < n_left; ++l) {
+        float a = 0.f;
+        for (int r = threadIdx.x; r < left_rows; r += blockDim.x) a += lstage[(size_t)l * left_rows + r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) s_left[l] = (s_warp[0] + s_warp[1]) + (s_warp[2] + s_warp[3]);
+        __syncthreads();
+      }
+    }
+    __syncthreads();  // the stage is free for the next batch
   }
+  const float sv[4] = {acc.x, acc.y, acc.z, acc.w};
   const int cols = max(ldwh, X ? ro.cols() : 0);
-  for (int f0 = threadIdx.x * 4; f0 < cols; f0 += blockDim.x * 4) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    bool have[4] = {false, false, false, false};
-    if (f0 + 4 <= F_main && (f0 >= f_last || f0 + 4 <= f_last)) {
-      const int n = (f0 >= f_last) ? S_last : S;  // columns of the last row group have their own split count
-      const float* p0 = P + (size_t)t * ldp + f0;
-      // every split's 16-byte load in flight at once (batches of kRB, predicated), summed in split order: one
-      // memory round trip per batch, deterministic result
-      constexpr int kRB = 20;
-      for (int k = 0; k < n; k += kRB) {
-        float4 v[kRB];
 #pragma unroll
-        for (int q = 0; q < kRB; ++q)
-          v[q] = (k + q < n) ? __ldcs(reinterpret_cast<const float4*>(p0 + (size_t)(k + q) * T * ldp))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int q = 0; q < kRB; ++q)
-          if (k + q < n) { s[0] += v[q].x; s[1] += v[q].y; s[2] += v[q].z; s[3] += v[q].w; }
-      }
-      have[0] = have[1] = have[2] = have[3] = true;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int f = f0 + j;
-        if (f < F_main) {
-          const int n = (f >= f_last) ? S_last : S;
-          for (int k = 0; k < n; ++k) s[j] += P[((size_t)k * T + t) * ldp + f];
-          have[j] = true;
-        } else if (f < F && left_rows > 0) {
-          s[j] = s_left[f - F_main];
-          have[j] = true;
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int f = f0 + j;
-      if (f < ldwh && (have[j] || f >= F)) WH[(size_t)t * ldwh + f] = s[j];
-      if (X) {
-        const float r = (have[j] && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s[j], eps)) : 0.f;
-        store_r(ro, t, f, r);
-      }
+  for (int j = 0; j < 4; ++j) {
+    const int f = c0 + col + j;
+    if (f >= cols) break;
+    float s = 0.f;
+    bool have = false;
+    if (f < F_main) { s = sv[j]; have = true; }
+    else if (f < F && left_rows > 0) { s = s_left[f - F_main]; have = true; }
+    if (f < ldwh && (have || f >= F)) WH[(size_t)t * ldwh + f] = s;
+    if (X) {
+      const float r = (have && f < F) ? __fdiv_rn(X[(size_t)t * ldx + f], fmaxf(s, eps)) : 0.f;
+      store_r(ro, t, f, r);
     }
   }
 }
@@ -719,8 +732,33 @@ leftover_rows_kernel(const float* __restrict__ H, int ldh, int T, int N, const f
   float acc[8];
 #pragma unroll
   for (int l = 0; l < 8; ++l) acc[l] = 0.f;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    const float h = H[(size_t)t * ldh + n];
+  const float* hrow = H + (size_t)t * ldh;
+  // 16-byte loads, four per thread in flight (rows are 16-byte aligned for every H / A^T this library allocates)
+  const bool vec = ((((uintptr_t)hrow) | ((uintptr_t)a)) & 15) == 0 && (lda & 3) == 0;
+  const int n4 = vec ? (N >> 2) : 0;
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * blockDim.x) {
+    float4 h[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + q * blockDim.x;
+      h[q] = i < n4 ? __ldcs(reinterpret_cast<const float4*>(hrow) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      if (l >= n_left) break;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * blockDim.x;
+        if (i < n4) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(a + (size_t)l * lda) + i);
+          acc[l] = fmaf(h[q].x, w.x, acc[l]); acc[l] = fmaf(h[q].y, w.y, acc[l]);
+          acc[l] = fmaf(h[q].z, w.z, acc[l]); acc[l] = fmaf(h[q].w, w.w, acc[l]);
+        }
+      }
+    }
+  }
+  for (int n = (n4 << 2) + threadIdx.x; n < N; n += blockDim.x) {
+    const float h = hrow[n];
 #pragma unroll
     for (int l = 0; l < 8; ++l)
       if (l < n_left) acc[l] = fmaf(h, a[(size_t)l * lda + n], acc[l]);
@@ -1145,19 +1183,29 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   const bool standalone = o.n_left > 0 && !from_partials;
   {
     ProfScope ps(1, s);
-    dim3 g(T, 1);
     const bool fuse = ra && !standalone;
+    const ROut ro = fuse ? ratio_out(o, mode, ra->R, ra->ldR) : ROut{};
+    const int cols = std::max(ldWH, fuse ? ro.cols() : 0);
+    const int lrows = from_partials ? left_rows(o) : 0;
+    const int batch = std::max(1, std::min(kRedMaxBatch, pl.max_splits));
+    const size_t smem = ((size_t)batch * kRedCols + (size_t)o.n_left * lrows) * sizeof(float);
+    static bool configured[64] = {false};
+    int dev = 0;
+    EVC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      EVC_CUDA(cudaFuncSetAttribute(reduce_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    if (smem > 160 * 1024) return fail(EVC_ERR_UNSUPPORTED, "split-K reduction: %zu bytes of staging exceed shared memory", smem);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = g; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cfg.gridDim = dim3(T, ceil_div(cols, kRedCols)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
-    const ROut ro = fuse ? ratio_out(o, mode, ra->R, ra->ldR) : ROut{};
     EVC_CUDA(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, (const float*)partials, pl.splits, pl.splits_last, pl.f_last, T,
-                                pl.ldp, o.F, o.F_main, WH, ldWH, (const float*)leftp, from_partials ? left_rows(o) : 0,
-                                o.n_left, left_ld(T), fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0,
-                                fuse ? ra->eps : 0.f, ro));
+                                pl.ldp, o.F, o.F_main, WH, ldWH, (const float*)leftp, lrows, o.n_left, left_ld(T),
+                                fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0, fuse ? ra->eps : 0.f, ro, batch));
     EVC_LAUNCH_CHECK();
     if (standalone) {
       const float* rows = (mode == EVC_MODE_TF32) ? (target ? o.BT : o.AT) + (size_t)o.F_main * o.ldN

@@ -133,6 +133,15 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtens
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16): no tensor map, no per-lane requests, so not
+// limited by the SM's outstanding-miss capacity the way LDG is.
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar), "l"(hint)
+      : "memory");
+}
+
 // Prefetch a 2-D tile into L2 only (no shared-memory destination): hides the HBM part of a later tma_load_2d.
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),

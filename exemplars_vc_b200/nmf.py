@@ -24,7 +24,7 @@ from typing import Optional
 
 import numpy as np
 
-from .dictionary import ExemplarDictionary
+from .dictionary import ExemplarDictionary, dictionary_cache
 
 try:  # so that filters written for the reference keep working when scikit-learn is around
     from sklearn.exceptions import ConvergenceWarning
@@ -35,6 +35,7 @@ except Exception:  # pragma: no cover - sklearn is not a dependency of the produ
 
 
 DEFAULT_MODE = "3xtf32"
+cache_dictionaries = True      # keep uploaded dictionaries resident between calls (content-checked, see DictionaryCache)
 
 
 def _check_dictionary_dtype(X: np.ndarray, H: np.ndarray):
@@ -47,7 +48,7 @@ def non_negative_factorization(X, W=None, H=None, n_components="auto", *, init=N
                                beta_loss="frobenius", tol=1e-4, max_iter=200, alpha_W=0.0, alpha_H="same",
                                l1_ratio=0.0, random_state=None, verbose=0, shuffle=False,
                                mode: str = DEFAULT_MODE, dictionary: Optional[ExemplarDictionary] = None,
-                               sklearn_l1_accumulate: bool = True):
+                               sklearn_l1_accumulate: bool = True, _device_result: Optional[dict] = None):
     """Fixed-dictionary NMF activations on the GPU.
 
     Returns ``(W, H, n_iter)`` with ``W`` (n_samples, n_components) the activations (frames are rows,
@@ -107,12 +108,16 @@ def non_negative_factorization(X, W=None, H=None, n_components="auto", *, init=N
         raise NotImplementedError("l2 regularisation (alpha_W with l1_ratio < 1) is not implemented")
     lam, lam_step = (0.0, l1_reg_W) if (sklearn_l1_accumulate and beta == "kullback-leibler") else (l1_reg_W, 0.0)
 
-    own = dictionary is None
-    d = ExemplarDictionary(H_arr, None, mode=mode) if own else dictionary
+    # the dictionary stays resident across calls with the same (unchanged) array: dictionary.DictionaryCache
+    own = dictionary is None and not cache_dictionaries
+    d = dictionary if dictionary is not None else (
+        ExemplarDictionary(H_arr, None, mode=mode) if own else dictionary_cache.get(H_arr, None, mode))
     try:
         t0 = time.time()
         act = d.solve(X_in, beta_loss=beta, tol=tol, max_iter=max_iter, lam=lam, lambda_step=lam_step)
         W_out = d.to_host(act.H).astype(X_in.dtype, copy=False)
+        if _device_result is not None and not own:     # script-level callers go on with the device-resident result
+            _device_result.update(dictionary=d, activation=act)
         if verbose:
             print("Epoch %02d reached after %.3f seconds, error: %f" % (act.n_iter, time.time() - t0, act.objective))
     finally:

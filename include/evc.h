@@ -171,6 +171,29 @@ int evc_gather_stack(const float* frames, int ld, int n_frames, int F, const int
                      int n_out, int context, float* out, int ld_out, void* stream);
 
 /*
+ * The step right after the path.
+ *
+ * WORLD-branch residual compensation as epilogues of the two products:
+ *   evc_residual:          R (T,F) = log(H A - X)                       04_align_n_nmf.py:292-294
+ *   evc_convert_residual:  Y (T,F) = exp(log(H B) + log(R')), R' = R with NaN -> 0       04_align_n_nmf.py:363-373
+ * (IEEE semantics of the reference's numpy expression: NaN where H A < X, Y = 0 where R' = 0, NaN where R' < 0).
+ *
+ * Griffin-Lim vocoder of the STFT branch (zz_audio_utilities.py:258-292, called with fft_size 400, hop 80,
+ * 300 iterations at 04_align_n_nmf.py:187), in double precision like the reference: device pointers, `window` =
+ * fft_size doubles (np.hanning(fft_size)), signals of T*hop + fft_size samples, x0 = the start signal (the
+ * reference draws np.random.randn), mag (T, fft_size/2+1) float.  sq_diff (iterations doubles, may be NULL) receives
+ * sum (x_new - x_prev)^2 per iteration (the RMSE the reference prints is sqrt(sq_diff / len)).  evc_stft / evc_istft
+ * are zz_audio_utilities.py:181-196 / 199-218; spec is (T, fft_size/2+1, 2) doubles (re, im).
+ */
+int evc_residual(evc_dict_t d, const float* X, int ldX, int T, const float* H, int ldH, float* R, int ldR, void* stream);
+int evc_convert_residual(evc_dict_t d, const float* H, int ldH, int T, const float* R, int ldR, float* Y, int ldY,
+                         void* stream);
+int evc_griffin_lim(const float* mag, int ldm, int T, int fft_size, int hop, int iterations, const double* window,
+                    const double* x0, double* x_out, double* sq_diff, void* stream);
+int evc_stft(const double* x, long long len, int fft_size, int hop, const double* window, double* spec, void* stream);
+int evc_istft(const double* spec, int T, int fft_size, int hop, const double* window, double* x_out, void* stream);
+
+/*
  * Optional: replace the NCCL all-reduce of the exemplar-sharded path by libevc_b200's own kernel over NVLink peer
  * memory (one node, 2..8 ranks, one process per GPU).  Every rank calls evc_p2p_alloc (allocates the exchange buffer
  * for up to max_frames frames and returns a 64-byte CUDA IPC handle), the handles of all ranks are exchanged by the

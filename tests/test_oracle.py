@@ -124,3 +124,18 @@ def test_real_speech_fixture_reduced_config1():
     assert abs(obj - float(g["objective"])) / float(g["objective"]) < 1e-9
     assert rel_fro(o.convert(W, B), g["Y"]) < 1e-6
     assert (W < 1e-6 * W.max()).mean() > 0.5     # activations of real speech over exemplars are sparse
+
+
+def test_griffin_lim_oracle_is_bit_identical_to_the_reference_functions():
+    """oracle/griffin_lim_oracle.py against outputs of the reference's own zz_audio_utilities.py functions
+    (oracle/make_golden_griffin_lim.py: the unmodified file imported with a numpy stand-in for pylab)."""
+    from conftest import load_golden
+    from oracle import griffin_lim_oracle as g
+    z = load_golden("griffin_lim_400_80")
+    fft, hop = int(z["fft_size"]), int(z["hop"])
+    S = g.stft_for_reconstruction(z["sig"], fft, hop)
+    assert np.array_equal(S.real, z["stft_re"]) and np.array_equal(S.imag, z["stft_im"])
+    assert np.array_equal(g.istft_for_reconstruction(S, fft, hop), z["istft"])
+    for it in (1, 3, 30):
+        x = g.reconstruct_signal_griffin_lim(z["mag"].astype(np.float64), fft, hop, it, z["x0"])
+        assert np.array_equal(x, z["x%d" % it])
