@@ -447,8 +447,12 @@ def main():
             sampler.start()
         launches0 = _lib.kernel_launch_count()
     t0 = time.perf_counter()
+    e2e_each, e2e_enqueue = [], 0.0
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         act_e, yh, hh = step_e2e()
+        e2e_each.append(round((time.perf_counter() - t1) * 1e3, 3))
+        e2e_enqueue += float(_lib.lib().evc_last_enqueue_ms())
     barrier()
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
     if step_resident is None:
@@ -570,6 +574,7 @@ def main():
                 "objective": objective, "host_enqueue_ms_per_step": enqueue_ms / args.steps,
                 "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_step, "copy_ms": copy_ms,
+                        "ms_each_step": e2e_each, "host_enqueue_ms_per_step": e2e_enqueue / args.steps,
                         "h2d_bytes_per_step": int(x_pinned.numel() * 4),
                         "d2h_bytes_per_step": int(np.asarray(yh).size * 4 + np.asarray(hh).size * 4)}}
         if extra:

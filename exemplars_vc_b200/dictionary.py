@@ -369,7 +369,8 @@ class DictionaryCache:
 
     def get(self, A: np.ndarray, B: Optional[np.ndarray], mode: str) -> "ExemplarDictionary":
         key = (self._ident(A), self._ident(B), mode, torch.cuda.current_device())
-        sums = (self._checksum(A), self._checksum(B))
+        sa = self._checksum(A)
+        sums = (sa, sa if B is A else self._checksum(B))
         hit = self._entries.get(key)
         if hit is not None and hit[1] == sums and hit[0]._h.value:
             self._entries[key] = self._entries.pop(key)     # most recently used last
