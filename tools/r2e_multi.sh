@@ -2,7 +2,7 @@
 # multi-GPU visit: sharded tests, bench at N ranks with the exemplar-sharded extra line, reference arm under torchrun
 N=${1:-2}; out=gpurun_out; mkdir -p $out
 nvidia-smi -L | head -9
-timeout 900 python -m pytest tests/test_multigpu_gpu.py tests/test_audio_gpu.py -m gpu -q -s > $out/r2e_pytest_n$N.log 2>&1; echo "pytest rc=$?"; tail -n 6 $out/r2e_pytest_n$N.log
+[ "$2" = "notests" ] || { timeout 900 python -m pytest tests/test_multigpu_gpu.py -m gpu -q -s > $out/r2e_pytest_n$N.log 2>&1; echo "pytest rc=$?"; tail -n 6 $out/r2e_pytest_n$N.log; }
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 > $out/r2e_bench_n$N.json 2> $out/r2e_bench_n$N.err; echo "bench N=$N rc=$?"; tail -n 4 $out/r2e_bench_n$N.err
 python - $out/r2e_bench_n$N.json <<'PY'
