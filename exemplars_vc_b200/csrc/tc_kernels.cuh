@@ -258,11 +258,18 @@ __device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, ui
   }
 }
 
-template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, int kEpi>
+// kP = CTA pairs per cluster.  With kP > 1 the pairs of a cluster work on items that share one operand tile -- the
+// frame tile of the ratio in contraction 2 (kShareM = false: pair q takes dictionary-row group P*g + q), the
+// dictionary tile in contraction 1 (kShareM = true: pair q takes frame tile P*s + q) -- and every CTA fetches only a
+// 1/kP slice of that tile, multicasting it to the CTAs of the other pairs that hold the same half: L2 -> SM traffic
+// of the shared operand drops by kP (both contractions are bound by that traffic, profiles/r2c_*).  The ring slots
+// then move in lock step across the cluster: a slot is free when EVERY pair's MMAs have read it (kP commits).
+template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, int kEpi, int kP = 1, bool kShareM = false>
 __global__ void __launch_bounds__(
     (TileCfg<kMTiles, kBlockT, kPrec, kSplitN, kEpi != TEPI_PARTIAL, kEpi == TEPI_MU_FRO>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
                const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmQ, const GemmParams p) {
+  static_assert(kP == 1 || kP == 2 || kP == 4, "1, 2 or 4 CTA pairs per cluster");
   constexpr bool kFro = (kEpi == TEPI_MU_FRO);
   constexpr bool kStageH = (kEpi != TEPI_PARTIAL);
   using Cfg = TileCfg<kMTiles, kBlockT, kPrec, kSplitN, kStageH, kFro>;
@@ -286,7 +293,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;         // rank inside the CTA pair: 0 = leader (issues the MMAs)
+  const int q = (int)(crank >> 1);           // pair inside the cluster
+  const uint32_t leader = crank & ~1u;      // cluster rank of this pair's leader
   uint8_t* ring_ptr = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t ring = smem_u32(ring_ptr);
 
@@ -298,7 +308,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), Cfg::kFullArrivals);
       mbar_init(smem_u32(&bar_raw[i]), 1);
-      mbar_init(smem_u32(&bar_empty[i]), 1);
+      mbar_init(smem_u32(&bar_empty[i]), kP);  // one commit per pair of the cluster
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(smem_u32(&bar_acc_full[i]), 1);
@@ -322,9 +332,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   pdl_launch_dependents();
 
   const int num_items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
-  const int first_item = blockIdx.x / kCG, item_stride = gridDim.x / kCG;  // both CTAs of a pair walk the same items
-  // the leader's "full" barriers as shared::cluster addresses (stage i at + 8 i)
-  const uint32_t full_leader = mapa_rank(smem_u32(&bar_full[0]), 0);
+  // all CTAs of a cluster walk the same (cluster-level) items; pair q takes its own share of each (item_of)
+  const int first_item = blockIdx.x / (kCG * kP), item_stride = gridDim.x / (kCG * kP);
+  auto item_of = [&](int item) {
+    WorkItem w = decode_item(p, item, kBlockT);
+    if (kP > 1) {
+      if (kShareM) w.t_tile = w.t_tile * kP + q; else w.m_group = w.m_group * kP + q;
+    }
+    return w;
+  };
+  // the pair leader's "full" barriers as shared::cluster addresses (stage i at + 8 i); == local address & ~(1 << 24)
+  const uint32_t full_leader = mapa_rank(smem_u32(&bar_full[0]), leader);
+  // cluster ranks of the CTAs that hold the same half of the shared operand tile as this one; all CTAs; this pair
+  uint16_t mc_mask = 0;
+#pragma unroll
+  for (int qq = 0; qq < kP; ++qq) mc_mask |= (uint16_t)(1u << (2 * qq + (int)rank));
+  constexpr uint16_t kAllMask = (uint16_t)((1u << (kCG * kP)) - 1u);
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * q));
+  constexpr int kSlice = 128 / kP;  // rows of a shared-operand box this CTA fetches (and multicasts)
 
   if (warp == 0) {
     // ================= TMA producer (one thread in each CTA of the pair) =================
@@ -332,7 +357,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item, kBlockT);
+        const WorkItem w = item_of(item);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
         // (a half-width item still loads a kNRows-row box: the narrower MMA never reads the surplus rows)
         const int t0 = w.t_tile * kBlockT + w.t_off + (int)rank * (w.t_cols / kCG);
@@ -352,18 +377,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < kMTiles; ++i)
 #pragma unroll
-            for (int pl = 0; pl < Cfg::kPlanes; ++pl)
-              tma_load_2d_pair(sbase + (i * Cfg::kPlanes + pl) * Cfg::kMPlaneBytes, &tmM, kc,
-                               pl * p.m_plane_rows + m0 + i * Cfg::kRowsPerSub, full, kEvictNormal);
+            for (int pl = 0; pl < Cfg::kPlanes; ++pl) {
+              const uint32_t dst = sbase + (i * Cfg::kPlanes + pl) * Cfg::kMPlaneBytes;
+              const int row = pl * p.m_plane_rows + m0 + i * Cfg::kRowsPerSub;
+              if (kP > 1 && kShareM)
+                tma_load_2d_pair_mc(dst + q * kSlice * Cfg::kRowBytes, &tmM, kc, row + q * kSlice, full, mc_mask, kEvictNormal);
+              else
+                tma_load_2d_pair(dst, &tmM, kc, row, full, kEvictNormal);
+            }
           if (kSplitN) {
             const uint32_t rawb = smem_u32(&bar_raw[stage]);
             mbar_arrive_expect_tx(rawb, (uint32_t)Cfg::kRawBytes);
             tma_load_2d(sbase + Cfg::kOffRaw, &tmN, kc, t0, rawb, kEvictFirst);  // H is streamed: keep A^T in L2
           } else {
+            constexpr int kNSlice = Cfg::kNRows / kP;
 #pragma unroll
-            for (int pl = 0; pl < Cfg::kPlanes; ++pl)
-              tma_load_2d_pair(sbase + Cfg::kOffN + pl * Cfg::kNPlaneBytes, &tmN, kc, pl * p.n_plane_rows + t0, full,
-                               kEvictNormal);
+            for (int pl = 0; pl < Cfg::kPlanes; ++pl) {
+              const uint32_t dst = sbase + Cfg::kOffN + pl * Cfg::kNPlaneBytes;
+              const int row = pl * p.n_plane_rows + t0;
+              if (kP > 1 && !kShareM)
+                tma_load_2d_pair_mc(dst + q * kNSlice * Cfg::kRowBytes, &tmN, kc, row + q * kNSlice, full, mc_mask, kEvictNormal);
+              else
+                tma_load_2d_pair(dst, &tmN, kc, row, full, kEvictNormal);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -375,7 +411,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item, kBlockT);
+        const WorkItem w = item_of(item);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles);
         const int kb0 = w.kb0, kb1 = w.kb1;
         const uint32_t idesc = (w.t_cols == kBlockT) ? kIdesc : make_idesc(kFmt, 128 * kCG, (uint32_t)w.t_cols);
@@ -412,12 +448,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
               }
             }
           }
-          // frees the smem slot in both CTAs of the pair when these MMAs retire
-          mma_commit_2cta(smem_u32(&bar_empty[stage]));
+          // frees the smem slot when these MMAs retire -- in every CTA of the cluster (the other pairs multicast into
+          // this pair's slots, so they have to see them free too)
+          mma_commit_mc(smem_u32(&bar_empty[stage]), kAllMask);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        // accumulator complete -> epilogue warps of both CTAs
-        mma_commit_2cta(smem_u32(&bar_acc_full[acc]));
+        // accumulator complete -> epilogue warps of both CTAs of this pair
+        mma_commit_mc(smem_u32(&bar_acc_full[acc]), pair_mask);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -426,7 +463,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (lane == 0) {
       int hbase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item, kBlockT);
+        const WorkItem w = item_of(item);
         const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = 0; c < nch; ++c) {
@@ -448,7 +485,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (lane == 0) {
       int hbase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        const WorkItem w = decode_item(p, item, kBlockT);
+        const WorkItem w = item_of(item);
         const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
         for (int c = 0; c < nch; ++c) {
@@ -475,7 +512,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     int acc = 0, stage = 0, hbase = 0;
     uint32_t acc_phase = 0, phase = 0;
     for (int item = first_item; item < num_items; item += item_stride) {
-      const WorkItem w = decode_item(p, item, kBlockT);
+      const WorkItem w = item_of(item);
       const int m_group = w.m_group, split = w.split;
       const int t0 = w.t_tile * kBlockT + w.t_off;
       if (kSplitN) {
@@ -599,7 +636,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&bar_acc_empty[acc]), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&bar_acc_empty[acc]), leader));
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -900,48 +937,91 @@ inline bool use_pdl() {
   return on;
 }
 
-template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, int kEpi>
-inline int launch_tc(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const CUtensorMap& tmQ,
-                     const GemmParams& p, cudaStream_t s) {
-  using Cfg = TileCfg<kMTiles, kBlockT, kPrec, kSplitN, kEpi != TEPI_PARTIAL, kEpi == TEPI_MU_FRO>;
-  auto kern = tc_gemm_kernel<kMTiles, kBlockT, kPrec, kSplitN, kEpi>;
-  // the > 48 KB dynamic shared memory opt-in is per device
-  static bool configured[64] = {false};
-  int dev = 0;
-  EVC_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
-    EVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
-  const int items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
-  if (items <= 0) return EVC_OK;
-  const int slots = num_sms() / kCG;  // CTA pairs resident at once
-  const int grid = (items < slots ? items : slots) * kCG;
+// CTA pairs per cluster asked for by the environment (A/B runs) or the measured default; 1, 2 or 4.
+inline int env_pairs(const char* name, int dflt) {
+  const char* v = getenv(name);
+  const int pr = v ? atoi(v) : dflt;
+  return (pr == 2 || pr == 4) ? pr : 1;
+}
+
+// How many clusters of kCG * P CTAs of this kernel the CURRENT device holds at once (B200: 74 pairs, 33 clusters of
+// two pairs, 15 of four: tools/probe/cluster_probe.cu); without a device (host-only tests) the SM count decides.
+template <class Kern>
+inline int active_clusters(Kern kern, int threads, int smem, int P) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(Cfg::kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cfg.gridDim = dim3(kCG * P * 64);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.x = kCG * P;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 2 : 1;
-#ifdef EVC_INSTRUMENT
-  static const int dbg = getenv("EVC_DEBUG_FLAGS") ? atoi(getenv("EVC_DEBUG_FLAGS")) : 0;
-  GemmParams q = p;
-  q.debug_flags = dbg;
-  EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, q));
-#else
-  EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, p));
-#endif
-  EVC_LAUNCH_CHECK();
-  return EVC_OK;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return n;
 }
+
+template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, int kEpi, int kP = 1, bool kShareM = false>
+struct TcLaunch {
+  using Cfg = TileCfg<kMTiles, kBlockT, kPrec, kSplitN, kEpi != TEPI_PARTIAL, kEpi == TEPI_MU_FRO>;
+  // configure (per device) and return the number of clusters resident at once; 0 = this cluster size cannot run here
+  static int slots() {
+    static int cache[64];
+    static bool configured[64] = {false};
+    auto kern = tc_gemm_kernel<kMTiles, kBlockT, kPrec, kSplitN, kEpi, kP, kShareM>;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return num_sms() / (kCG * kP); }
+    if (!configured[dev]) {
+      // the > 48 KB dynamic shared memory opt-in is per device
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return num_sms() / (kCG * kP);
+      }
+      cache[dev] = (kP == 1) ? num_sms() / kCG : active_clusters(kern, Cfg::kThreads, Cfg::kSmemBytes, kP);
+      configured[dev] = true;
+    }
+    return cache[dev];
+  }
+  static int launch(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const CUtensorMap& tmQ,
+                    const GemmParams& p, cudaStream_t s) {
+    auto kern = tc_gemm_kernel<kMTiles, kBlockT, kPrec, kSplitN, kEpi, kP, kShareM>;
+    const int nslots = slots();
+    if (nslots <= 0) return fail(EVC_ERR_UNSUPPORTED, "clusters of %d CTA pairs cannot be scheduled on this device", kP);
+    const int items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
+    if (items <= 0) return EVC_OK;
+    const int grid = (items < nslots ? items : nslots) * kCG * kP;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCG * kP;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl() ? 2 : 1;
+#ifdef EVC_INSTRUMENT
+    static const int dbg = getenv("EVC_DEBUG_FLAGS") ? atoi(getenv("EVC_DEBUG_FLAGS")) : 0;
+    GemmParams qp = p;
+    qp.debug_flags = dbg;
+    EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, qp));
+#else
+    EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, p));
+#endif
+    EVC_LAUNCH_CHECK();
+    return EVC_OK;
+  }
+};
 
 // Tile shapes per contraction.
 constexpr int kC1MTiles = 2, kC1BlockT = 256;  // contraction 1 / conversion: 512 dictionary rows x 256 frames, split-K
@@ -949,7 +1029,7 @@ constexpr int kC2MTiles = 1, kC2BlockT = 256;  // contraction 2: 256 exemplars x
 // K elements per K-block of a mode (one swizzle row)
 inline int bk_elems(int mode) { return mode == EVC_MODE_BF16 ? 64 : 32; }
 // rows reserved per bf16 plane in a stacked operand: a multiple of every row-group size, so no TMA box straddles planes
-inline long long plane_rows(int rows) { return (long long)round_up(rows, 512); }
+inline long long plane_rows(int rows) { return (long long)round_up(rows, 1024); }
 
 // Resident tensor-core operands of one dictionary.
 struct DictOperands {
@@ -969,6 +1049,7 @@ struct DictOperands {
   long long a_rows = 0, at_rows = 0;
   __nv_bfloat16 *A16 = nullptr, *AT16 = nullptr, *BT16 = nullptr;
   CUtensorMap tmA16, tmAT16, tmBT16;
+  CUtensorMap tmAT16_s[2], tmBT16_s[2];  // the same with 64- and 32-row boxes: the slices clusters of 2 / 4 pairs multicast
   DevBuf h16, r16;  // per solve: bf16 shadow of H (BF16 mode); the ratio as bf16 / as two bf16 planes
   long long r_rows = 0;  // rows per plane of r16 in the split mode
   void release() {
@@ -1037,11 +1118,15 @@ inline int build_operands(DictOperands* o, int mode, const float* A, const float
   EVC_TRY(launch_to_bf16(o->AT, o->ldN, o->AT16, o->ldN16, o->F_main, N, planes == 2 ? at_elems : 0, s));
   EVC_TRY(make_tmap16(&o->tmA16, o->A16, planes * o->a_rows, F, o->ldA16, bk, 128));
   EVC_TRY(make_tmap16(&o->tmAT16, o->AT16, planes * o->at_rows, N, o->ldN16, bk, 128));
+  EVC_TRY(make_tmap16(&o->tmAT16_s[0], o->AT16, planes * o->at_rows, N, o->ldN16, bk, 64));
+  EVC_TRY(make_tmap16(&o->tmAT16_s[1], o->AT16, planes * o->at_rows, N, o->ldN16, bk, 32));
   if (B) {
     EVC_CUDA(cudaMalloc(&o->BT16, planes * at_elems * sizeof(__nv_bfloat16)));
     EVC_CUDA(cudaMemsetAsync(o->BT16, 0, planes * at_elems * sizeof(__nv_bfloat16), s));
     EVC_TRY(launch_to_bf16(o->BT, o->ldN, o->BT16, o->ldN16, o->F_main, N, planes == 2 ? at_elems : 0, s));
     EVC_TRY(make_tmap16(&o->tmBT16, o->BT16, planes * o->at_rows, N, o->ldN16, bk, 128));
+    EVC_TRY(make_tmap16(&o->tmBT16_s[0], o->BT16, planes * o->at_rows, N, o->ldN16, bk, 64));
+    EVC_TRY(make_tmap16(&o->tmBT16_s[1], o->BT16, planes * o->at_rows, N, o->ldN16, bk, 32));
   }
   // the fp32 transposes were staging only (stream order: the conversions above read them first)
   EVC_CUDA(cudaFreeAsync(o->AT, s));
@@ -1060,12 +1145,14 @@ struct C1Plan {
   int f_last;                          // first dictionary row of the last group
   int max_splits;
 };
-inline C1Plan plan_c1(int F, int N, int T, int bk) {
+// `pairs` = CTA pairs per cluster (they take `pairs` neighbouring frame tiles of one K range and share the dictionary
+// tile): the plan is made over frame SUPER-tiles and `slots` = clusters resident at once.
+inline C1Plan plan_c1(int F, int N, int T, int bk, int pairs = 1, int slots_in = 0) {
   C1Plan pl{};
   const int sub_rows = 128 * kCG;  // dictionary rows of one MMA
   const int tiles = ceil_div(F, sub_rows);
   pl.m_groups = ceil_div(tiles, kC1MTiles);
-  pl.t_tiles = ceil_div(T, kC1BlockT);
+  pl.t_tiles = ceil_div(ceil_div(T, kC1BlockT), pairs);
   pl.kb_total = ceil_div(N, bk);
   pl.ldp = round_up(F, 32);
   const int tiles_last = tiles - (pl.m_groups - 1) * kC1MTiles;
@@ -1073,7 +1160,7 @@ inline C1Plan plan_c1(int F, int N, int T, int bk) {
   const int full_groups = partial ? pl.m_groups - 1 : pl.m_groups;
   pl.f_last = partial ? full_groups * kC1MTiles * sub_rows : F;
   // w = sub-tile K-blocks per CTA pair; grow it until the items fit the SMs
-  const int slots = num_sms() / kCG;  // CTA pairs resident at once
+  const int slots = slots_in > 0 ? slots_in : num_sms() / (kCG * pairs);  // clusters resident at once
   long long total = (long long)tiles * pl.kb_total * pl.t_tiles;
   int w = (int)std::max<long long>(1, (total + slots - 1) / slots);
   for (;; ++w) {
@@ -1092,10 +1179,36 @@ inline C1Plan plan_c1(int F, int N, int T, int bk) {
   return pl;
 }
 
+// CTA pairs per cluster of the two contractions (fp32-accurate mode; the fast modes run plain pairs).  Defaults are
+// the measured best (profiles/r2_multicast_ab.txt); EVC_C1_PAIRS / EVC_C2_PAIRS = 1 | 2 | 4 override for A/B runs.
+#ifndef EVC_C1_PAIRS_DEFAULT
+#define EVC_C1_PAIRS_DEFAULT 1
+#endif
+#ifndef EVC_C2_PAIRS_DEFAULT
+#define EVC_C2_PAIRS_DEFAULT 1
+#endif
+inline int c1_slots_for(int P) {
+  if (P == 2) return TcLaunch<kC1MTiles, kC1BlockT, PREC_SPLIT, true, TEPI_PARTIAL, 2, true>::slots();
+  if (P == 4) return TcLaunch<kC1MTiles, kC1BlockT, PREC_SPLIT, true, TEPI_PARTIAL, 4, true>::slots();
+  return num_sms() / kCG;
+}
+inline int c1_pairs(int mode) {
+  static const int want = env_pairs("EVC_C1_PAIRS", EVC_C1_PAIRS_DEFAULT);
+  if (mode != EVC_MODE_3XTF32 || want == 1) return 1;
+  return c1_slots_for(want) > 0 ? want : 1;  // a device that cannot co-schedule such clusters runs plain pairs
+}
+inline int c2_pairs(int mode) {
+  static const int want = env_pairs("EVC_C2_PAIRS", EVC_C2_PAIRS_DEFAULT);
+  return (mode == EVC_MODE_3XTF32) ? want : 1;
+}
+struct DictOperands;
+inline C1Plan c1_plan(int F_main, int N, int T, int mode);
+
 // Called before a solve / product: make sure the workspace can hold the split-K partials.
 // Workspace layout: [ split-K partials | leftover-row partials of the fused update ].
 inline size_t ws_left_offset(const C1Plan& pl, int T) { return round_up_sz((size_t)pl.max_splits * T * pl.ldp, 64); }
-inline int left_rows(const DictOperands& o) { return round_up(ceil_div(o.N, 128), kCG) * 4; }
+// (rounded so that the padding row groups of a cluster of up to 4 pairs have somewhere to put their zeros)
+inline int left_rows(const DictOperands& o) { return round_up(ceil_div(o.N, 128), kCG * 4) * 4; }
 inline int left_ld(int T) { return round_up(T, kC2BlockT); }
 
 // Room for the K operand of contraction 2 (the ratio) in the mode's format; pad rows start out zero.
@@ -1123,9 +1236,14 @@ inline ROut ratio_out(DictOperands& o, int mode, float* R, int ldR) {
   return ro;
 }
 
+inline C1Plan c1_plan(int F_main, int N, int T, int mode) {
+  const int P = c1_pairs(mode);
+  return plan_c1(F_main, N, T, bk_elems(mode), P, c1_slots_for(P));
+}
+
 inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, int T, DevBuf* ws, cudaStream_t s) {
   if (mode == EVC_MODE_FP32) return EVC_OK;
-  const C1Plan pl = plan_c1(o.F_main, o.N, T, bk_elems(mode));
+  const C1Plan pl = c1_plan(o.F_main, o.N, T, mode);
   o.left_valid = false;
   const size_t left = (size_t)left_rows(o) * o.n_left * left_ld(T);
   EVC_TRY(ws->reserve((ws_left_offset(pl, T) + left) * sizeof(float)));
@@ -1152,12 +1270,12 @@ inline int launch_ratio(DictOperands& o, int mode, const float* X, int ldX, cons
   return EVC_OK;
 }
 
-template <int kPrec>
+template <int kPrec, int kP = 1>
 inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
                          DevBuf* ws, cudaStream_t s, const RatioArgs* ra) {
   constexpr bool kSplitN = (kPrec == PREC_SPLIT);
   const int bke = bk_elems(mode);
-  const C1Plan pl = plan_c1(o.F_main, o.N, T, bke);
+  const C1Plan pl = c1_plan(o.F_main, o.N, T, mode);
   float* partials = ws->as<float>();
   float* leftp = ws->as<float>() + ws_left_offset(pl, T);
   CUtensorMap tmH;
@@ -1175,8 +1293,10 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   p.out = partials; p.ld_out = pl.ldp;
   {
     ProfScope ps(0, s);
-    const CUtensorMap& tmD = (kPrec == PREC_TF32) ? (target ? o.tmBT : o.tmAT) : (target ? o.tmBT16 : o.tmAT16);
-    EVC_TRY((launch_tc<kC1MTiles, kC1BlockT, kPrec, kSplitN, TEPI_PARTIAL>(tmD, tmH, tmH, tmH, p, s)));
+    const CUtensorMap& tmD = (kPrec == PREC_TF32) ? (target ? o.tmBT : o.tmAT)
+                             : (kP == 1)          ? (target ? o.tmBT16 : o.tmAT16)
+                                                  : (target ? o.tmBT16_s[kP / 4] : o.tmAT16_s[kP / 4]);
+    EVC_TRY((TcLaunch<kC1MTiles, kC1BlockT, kPrec, kSplitN, TEPI_PARTIAL, kP, true>::launch(tmD, tmH, tmH, tmH, p, s)));
   }
   // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
   const bool from_partials = o.n_left > 0 && !target && o.left_valid;
@@ -1221,30 +1341,40 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
 inline int contract_wh(DictOperands& o, int mode, const float* H, int ldH, int T, float* WH, int ldWH, bool target,
                        DevBuf* ws, cudaStream_t s, const RatioArgs* ra = nullptr) {
   if (target && !o.has_target) return fail(EVC_ERR_INVALID_ARGUMENT, "no target dictionary");
-  if (mode == EVC_MODE_3XTF32) return contract_wh_t<PREC_SPLIT>(o, mode, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  if (mode == EVC_MODE_3XTF32) {
+    const int P = c1_pairs(mode);
+    if (P == 2) return contract_wh_t<PREC_SPLIT, 2>(o, mode, H, ldH, T, WH, ldWH, target, ws, s, ra);
+    if (P == 4) return contract_wh_t<PREC_SPLIT, 4>(o, mode, H, ldH, T, WH, ldWH, target, ws, s, ra);
+    return contract_wh_t<PREC_SPLIT>(o, mode, H, ldH, T, WH, ldWH, target, ws, s, ra);
+  }
   if (mode == EVC_MODE_BF16) return contract_wh_t<PREC_BF16>(o, mode, H, ldH, T, WH, ldWH, target, ws, s, ra);
   return contract_wh_t<PREC_TF32>(o, mode, H, ldH, T, WH, ldWH, target, ws, s, ra);
 }
 
 // Second contraction with a fused epilogue.  `R` is what multiplies A^T: the ratio (KL) or A H (Frobenius); in the
 // split / bf16 modes it lives in o.r16 (made by the reduction / ratio kernels).
-template <int kPrec, int kEpi>
+template <int kPrec, int kEpi, int kP = 1>
 inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR, GemmParams p, const float* num0,
                        cudaStream_t s) {
+  using Launch = TcLaunch<kC2MTiles, kC2BlockT, kPrec, false, kEpi, kP, false>;
+  if (kP > 1 && Launch::slots() <= 0)  // this device cannot co-schedule such clusters: plain pairs
+    return contract2_p<kPrec, kEpi, 1>(o, mode, T, R, ldR, p, num0, s);
   const int bke = bk_elems(mode);
   const int planes = (kPrec == PREC_SPLIT) ? 2 : 1;
   CUtensorMap tmR;
+  // (clusters of kP pairs: every CTA fetches a 1/kP slice of its half of the frame tile and multicasts it)
   if (kPrec == PREC_TF32) EVC_TRY(make_tmap(&tmR, R, T, o.F, ldR, 32, kC2BlockT / kCG));
   else EVC_TRY(make_tmap16(&tmR, o.r16.as<__nv_bfloat16>(), kPrec == PREC_SPLIT ? planes * o.r_rows : (long long)T, o.F,
-                           o.ldA16, bke, kC2BlockT / kCG));
+                           o.ldA16, bke, kC2BlockT / kCG / kP));
   p.M_total = o.N; p.T = T; p.K = o.F;
-  p.num_m_groups = ceil_div(o.N, 128 * kC2MTiles * kCG); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
+  // row groups of 256 exemplars, dealt to the pairs of a cluster in runs of kP: the work items are cluster-level
+  p.num_m_groups = ceil_div(ceil_div(o.N, 128 * kC2MTiles * kCG), kP); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(o.F, bke); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
   p.m_plane_rows = (int)o.a_rows; p.n_plane_rows = (int)o.r_rows;
   {
     // tail balancing: the tiles of a last, less-than-half-filled round run as two half-width items each
-    const int slots = num_sms() / kCG, rem = p.items_main % slots;
+    const int slots = Launch::slots(), rem = p.items_main % slots;
     static const bool allow = getenv("EVC_NO_HALF_TILES") == nullptr;
     p.half_from = (allow && p.items_main > slots && rem > 0 && 2 * rem <= slots) ? p.items_main - rem : p.items_main;
   }
@@ -1255,20 +1385,25 @@ inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR
   if (kEpi != TEPI_PARTIAL) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
   if (kEpi == TEPI_MU_FRO) EVC_TRY(make_tmap(&tmQc, num0, T, o.N, p.ld_out, 128, kHChunkT, false));
   ProfScope ps(2, s);
-  return launch_tc<kC2MTiles, kC2BlockT, kPrec, false, kEpi>(kPrec == PREC_TF32 ? o.tmA : o.tmA16, tmR, tmHc, tmQc, p, s);
+  return Launch::launch(kPrec == PREC_TF32 ? o.tmA : o.tmA16, tmR, tmHc, tmQc, p, s);
 }
 
 template <int kEpi>
 inline int contract2_t(DictOperands& o, int mode, int T, const float* R, int ldR, const GemmParams& p, const float* num0,
                        cudaStream_t s) {
-  if (mode == EVC_MODE_3XTF32) return contract2_p<PREC_SPLIT, kEpi>(o, mode, T, R, ldR, p, num0, s);
+  if (mode == EVC_MODE_3XTF32) {
+    const int P = c2_pairs(mode);
+    if (P == 2) return contract2_p<PREC_SPLIT, kEpi, 2>(o, mode, T, R, ldR, p, num0, s);
+    if (P == 4) return contract2_p<PREC_SPLIT, kEpi, 4>(o, mode, T, R, ldR, p, num0, s);
+    return contract2_p<PREC_SPLIT, kEpi>(o, mode, T, R, ldR, p, num0, s);
+  }
   if (mode == EVC_MODE_BF16) return contract2_p<PREC_BF16, kEpi>(o, mode, T, R, ldR, p, num0, s);
   return contract2_p<PREC_TF32, kEpi>(o, mode, T, R, ldR, p, num0, s);
 }
 
 inline void left_args(DictOperands& o, int mode, int T, DevBuf* ws, GemmParams& p) {
   if (o.n_left <= 0) return;
-  const C1Plan pl = plan_c1(o.F_main, o.N, T, bk_elems(mode));
+  const C1Plan pl = c1_plan(o.F_main, o.N, T, mode);
   p.left_a = (mode == EVC_MODE_TF32) ? o.AT + (size_t)o.F_main * o.ldN : o.ATleft;
   p.left_lda = o.ldN; p.n_left = o.n_left;
   p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T); p.left_rows = left_rows(o);

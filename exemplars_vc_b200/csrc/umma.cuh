@@ -133,6 +133,19 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtens
       : "memory");
 }
 
+// ... and the same with .multicast::cluster: the box lands at the same CTA-relative offset in every CTA of `mask`, and
+// the bytes are credited to the barrier at `bar`'s offset in the LEADER of each destination CTA's pair (bar = a
+// CTA-local address with the pair bit cleared, `addr & 0xFEFFFFFF`: shared::cluster addresses are rank << 24 | offset,
+// tools/probe/cluster_probe.cu) -- one L2 read feeds several SMs.
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t smem_dst, const CUtensorMap* m, int c0, int c1,
+                                                    uint32_t bar, uint16_t mask, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask), "l"(hint)
+      : "memory");
+}
+
 // 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16): no tensor map, no per-lane requests, so not
 // limited by the SM's outstanding-miss capacity the way LDG is.
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t hint) {
@@ -236,6 +249,13 @@ __device__ __forceinline__ void mma_issue(uint32_t tmem_d, uint64_t adesc, uint6
     if (kCG == 2) mma_tf32_2cta(tmem_d, adesc, bdesc, idesc, accumulate);
     else mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
   }
+}
+// arrive on the barrier at this shared-memory offset in every CTA of `mask` (cluster ranks) when the MMAs retire
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
 }
 // arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair when the MMAs retire
 __device__ __forceinline__ void mma_commit_2cta(uint32_t bar) {

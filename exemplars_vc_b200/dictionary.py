@@ -368,6 +368,8 @@ class DictionaryCache:
         return (total + int(flat[n8:].sum(dtype=np.uint64)) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
     def get(self, A: np.ndarray, B: Optional[np.ndarray], mode: str) -> "ExemplarDictionary":
+        if not torch.cuda.is_available():
+            raise RuntimeError("exemplars_vc_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         key = (self._ident(A), self._ident(B), mode, torch.cuda.current_device())
         sa = self._checksum(A)
         sums = (sa, sa if B is A else self._checksum(B))

@@ -24,8 +24,13 @@ static int fails = 0;
   } while (0)
 
 // contraction 1: the parameters contract_wh_t derives from the plan
-static void check_c1(int F_main, int N, int T, int bke) {
-  const C1Plan pl = plan_c1(F_main, N, T, bke);
+// `pairs` CTA pairs per cluster share the dictionary tile and take neighbouring frame tiles: the plan is made over
+// frame super-tiles and `slots` clusters (B200: 74 / 33 / 15 for 1 / 2 / 4 pairs, tools/probe/cluster_probe.cu)
+static void check_c1(int F_main, int N, int T, int bke, int pairs = 1, int slots = 0) {
+  const C1Plan pl = plan_c1(F_main, N, T, bke, pairs, slots);
+  CHECK(pl.t_tiles == ceil_div(ceil_div(T, kC1BlockT), pairs), "super-tiles");
+  CHECK(slots == 0 || (long long)pl.t_tiles * ((pl.splits_last ? pl.m_groups - 1 : pl.m_groups) * pl.splits + pl.splits_last) <= slots ||
+            (pl.splits <= 1 && pl.splits_last <= 1), "one wave of clusters");
   GemmParams p{};
   p.M_total = F_main; p.T = T; p.K = N;
   p.num_m_groups = pl.m_groups; p.num_t_tiles = pl.t_tiles; p.num_splits = pl.splits;
@@ -105,6 +110,7 @@ int main() {
       const int F = s[0], N = s[1], T = s[2];
       const int n_left = (F > 128 && (F % 128) <= 8) ? F % 128 : 0;
       check_c1(F - n_left, N, T, bke); check_c2(N, T, F, bke); ++n;
+      check_c1(F - n_left, N, T, bke, 2, 33); check_c1(F - n_left, N, T, bke, 4, 15);
     }
   for (int i = 0; i < 3000; ++i) {
     const int F = 1 + (int)(rng() % 3000), N = 1 + (int)(rng() % (i % 7 == 0 ? 300000 : 30000)), T = 1 + (int)(rng() % (i % 11 == 0 ? 140000 : 3000));
@@ -112,6 +118,7 @@ int main() {
     const int n_left = (F > 128 && (F % 128) <= 8) ? F % 128 : 0;
     if (F - n_left < 1) continue;
     check_c1(F - n_left, N, T, bke); check_c2(N, T, F, bke); ++n;
+    if (i % 3 == 0) { check_c1(F - n_left, N, T, bke, 2, 33); check_c1(F - n_left, N, T, bke, 4, 15); }
   }
   printf("plan_check: %d shapes, %d failures (cta_group %d, %d SMs assumed)\n", n, fails, cta_group(), num_sms());
   return fails ? 1 : 0;
