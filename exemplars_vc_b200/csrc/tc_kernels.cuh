@@ -84,6 +84,7 @@ struct GemmParams {
   int left_lda, n_left;
   float* left_out;      // [l][t][row] partial sums, row = 4*(128-exemplar block) + lane quarter
   int left_ld, left_rows;  // frames pitch, rows pitch
+  int out_keep_l2;      // PARTIAL: store with the L2 evict-last hint (split-K partials: the reduction reads them next)
   int debug_flags;      // -DEVC_INSTRUMENT builds only (tools/flag_sweep.sh); always 0 and never read otherwise
 };
 
@@ -624,7 +625,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           // whole chunk in range and every lane a real row: straight-line code
           const bool fast = (tb + 32 <= p.T) && rows_full;
           float* o = p.out + ((size_t)split * p.T + tb) * p.ld_out + m;
-          if (fast) {
+          if (fast && p.out_keep_l2) {
+            // split-K partials: 37 MB that the reduction kernel reads right after this one -- keep them in L2 (they
+            // were evicted by the streamed operands and came back from DRAM: 16 % L2 hits, profiles/r2c_*)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st_global_hint(o + (size_t)j * p.ld_out, __uint_as_float(v[j]), kEvictLast);
+          } else if (fast) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[(size_t)j * p.ld_out] = __uint_as_float(v[j]);
           } else {
@@ -1291,6 +1297,7 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   p.half_from = p.items_main;
   p.m_plane_rows = (int)o.at_rows; p.n_plane_rows = 0;
   p.out = partials; p.ld_out = pl.ldp;
+  p.out_keep_l2 = getenv("EVC_NO_KEEP_L2") ? 0 : 1;
   {
     ProfScope ps(0, s);
     const CUtensorMap& tmD = (kPrec == PREC_TF32) ? (target ? o.tmBT : o.tmAT)

@@ -175,6 +175,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // all committed stores are complete (globally visible at kernel end)
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// fp32 store with an L2 eviction-priority hint (same 64-bit policy words as the TMA hints)
+__device__ __forceinline__ void st_global_hint(float* p, float v, uint64_t hint) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(hint) : "memory");
+}
+
 // ---- tcgen05 -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
