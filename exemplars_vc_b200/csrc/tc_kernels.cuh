@@ -1203,9 +1203,15 @@ inline int c1_pairs(int mode) {
   if (mode != EVC_MODE_3XTF32 || want == 1) return 1;
   return c1_slots_for(want) > 0 ? want : 1;  // a device that cannot co-schedule such clusters runs plain pairs
 }
+inline int c2_slots_for(int P) {
+  if (P == 2) return TcLaunch<kC2MTiles, kC2BlockT, PREC_SPLIT, false, TEPI_MU_KL, 2, false>::slots();
+  if (P == 4) return TcLaunch<kC2MTiles, kC2BlockT, PREC_SPLIT, false, TEPI_MU_KL, 4, false>::slots();
+  return num_sms() / kCG;
+}
 inline int c2_pairs(int mode) {
   static const int want = env_pairs("EVC_C2_PAIRS", EVC_C2_PAIRS_DEFAULT);
-  return (mode == EVC_MODE_3XTF32) ? want : 1;
+  if (mode != EVC_MODE_3XTF32 || want == 1) return 1;
+  return c2_slots_for(want) > 0 ? want : 1;
 }
 struct DictOperands;
 inline C1Plan c1_plan(int F_main, int N, int T, int mode);
@@ -1213,8 +1219,10 @@ inline C1Plan c1_plan(int F_main, int N, int T, int mode);
 // Called before a solve / product: make sure the workspace can hold the split-K partials.
 // Workspace layout: [ split-K partials | leftover-row partials of the fused update ].
 inline size_t ws_left_offset(const C1Plan& pl, int T) { return round_up_sz((size_t)pl.max_splits * T * pl.ldp, 64); }
-// (rounded so that the padding row groups of a cluster of up to 4 pairs have somewhere to put their zeros)
-inline int left_rows(const DictOperands& o) { return round_up(ceil_div(o.N, 128), kCG * 4) * 4; }
+// One partial per 32 exemplars, for every 128-row block some CTA of contraction 2 works on -- with P pairs per
+// cluster the row groups come in runs of P, so the padding groups of the last run write (zero) partials too; every
+// entry the reduction sums is therefore written by every fused update.
+inline int left_rows(const DictOperands& o, int mode) { return round_up(ceil_div(o.N, 128), kCG * c2_pairs(mode)) * 4; }
 inline int left_ld(int T) { return round_up(T, kC2BlockT); }
 
 // Room for the K operand of contraction 2 (the ratio) in the mode's format; pad rows start out zero.
@@ -1251,7 +1259,7 @@ inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, i
   if (mode == EVC_MODE_FP32) return EVC_OK;
   const C1Plan pl = c1_plan(o.F_main, o.N, T, mode);
   o.left_valid = false;
-  const size_t left = (size_t)left_rows(o) * o.n_left * left_ld(T);
+  const size_t left = (size_t)left_rows(o, mode) * o.n_left * left_ld(T);
   EVC_TRY(ws->reserve((ws_left_offset(pl, T) + left) * sizeof(float)));
   EVC_TRY(reserve_ratio(o, mode, T, s));
   if (mode == EVC_MODE_BF16) {
@@ -1313,7 +1321,7 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
     const bool fuse = ra && !standalone;
     const ROut ro = fuse ? ratio_out(o, mode, ra->R, ra->ldR) : ROut{};
     const int cols = std::max(ldWH, fuse ? ro.cols() : 0);
-    const int lrows = from_partials ? left_rows(o) : 0;
+    const int lrows = from_partials ? left_rows(o, mode) : 0;
     const int batch = std::max(1, std::min(kRedMaxBatch, pl.max_splits));
     const size_t smem = ((size_t)batch * kRedCols + (size_t)o.n_left * lrows) * sizeof(float);
     static bool configured[64] = {false};
@@ -1413,7 +1421,7 @@ inline void left_args(DictOperands& o, int mode, int T, DevBuf* ws, GemmParams& 
   const C1Plan pl = c1_plan(o.F_main, o.N, T, mode);
   p.left_a = (mode == EVC_MODE_TF32) ? o.AT + (size_t)o.F_main * o.ldN : o.ATleft;
   p.left_lda = o.ldN; p.n_left = o.n_left;
-  p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T); p.left_rows = left_rows(o);
+  p.left_out = ws->as<float>() + ws_left_offset(pl, T); p.left_ld = left_ld(T); p.left_rows = left_rows(o, mode);
   o.left_valid = true;  // (stream order: the partials are complete before the next contraction 1 reads them)
 }
 
