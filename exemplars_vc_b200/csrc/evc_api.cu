@@ -161,8 +161,8 @@ int objective_segments(evc_dict* d, const float* X, int ldX, int T, const float*
   EVC_TRY(contract_wh(d, H, ldH, T, wh_buf(d), d->ldWH, false, s));
   {
     ProfScope ps(3, s);
-    simt::objective_rows_kernel<<<ceil_div(T, 8), 256, 0, s>>>(X, ldX, wh_buf(d), d->ldWH, T, d->F, eps, loss,
-                                                              d->rowd.as<double>());
+    simt::objective_rows_kernel<<<ceil_div(T, simt::kObjRowsPerBlock), simt::kObjWarpsPerRow * simt::kObjRowsPerBlock * 32, 0, s>>>(
+        X, ldX, wh_buf(d), d->ldWH, T, d->F, eps, loss, d->rowd.as<double>());
     EVC_LAUNCH_CHECK();
   }
   EVC_CUDA(cudaMemcpyAsync(d->host_rows, d->rowd.p, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -200,29 +200,38 @@ __global__ void ratio_kernel(const float* __restrict__ X, int ldx, const float* 
 //   sum_{X>eps} X log(X / max(WH,eps)) - sum_{X>eps} X + sum_all WH
 // (sklearn forms sum_all WH as dot(W.sum(0), A.sum(1)); it is the same number up to rounding.)
 // loss == FROBENIUS: sum (X - WH)^2.
-__global__ void objective_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ WH, int ldwh,
-                                      int T, int F, float eps, int loss, double* __restrict__ rowobj) {
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
-  const int lane = threadIdx.x & 31;
+// Four warps per frame (a double-precision log per element: with one warp per frame a 513-bin frame was a serial
+// chain of 16 logs per lane and the kernel took 17 us, profiles/r2g_*); the four warp sums are added in a fixed order.
+constexpr int kObjWarpsPerRow = 4, kObjRowsPerBlock = 2;
+__global__ void __launch_bounds__(kObjWarpsPerRow * kObjRowsPerBlock * 32)
+objective_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ WH, int ldwh, int T, int F,
+                      float eps, int loss, double* __restrict__ rowobj) {
+  __shared__ double part[kObjRowsPerBlock][kObjWarpsPerRow];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = warp / kObjWarpsPerRow, w = warp % kObjWarpsPerRow;
+  const int t = blockIdx.x * kObjRowsPerBlock + r;
   double s = 0.0;
-  for (int f = lane; f < F; f += 32) {
-    const float x = X[(size_t)t * ldx + f];
-    const float wh = WH[(size_t)t * ldwh + f];
-    if (loss == EVC_LOSS_KL) {
-      double term = (double)wh;
-      if (x > eps) {
-        const double whc = (double)fmaxf(wh, eps);
-        term += (double)x * log((double)x / whc) - (double)x;
+  if (t < T) {
+    for (int f = w * 32 + lane; f < F; f += 32 * kObjWarpsPerRow) {
+      const float x = X[(size_t)t * ldx + f];
+      const float wh = WH[(size_t)t * ldwh + f];
+      if (loss == EVC_LOSS_KL) {
+        double term = (double)wh;
+        if (x > eps) {
+          const double whc = (double)fmaxf(wh, eps);
+          term += (double)x * log((double)x / whc) - (double)x;
+        }
+        s += term;
+      } else {
+        const double d = (double)x - (double)wh;
+        s += d * d;
       }
-      s += term;
-    } else {
-      const double d = (double)x - (double)wh;
-      s += d * d;
     }
   }
   s = warp_sum(s);
-  if (lane == 0) rowobj[t] = s;
+  if (lane == 0) part[r][w] = s;
+  __syncthreads();
+  if (w == 0 && lane == 0 && t < T) rowobj[t] = (part[r][0] + part[r][1]) + (part[r][2] + part[r][3]);
 }
 
 // dst (rows, ld_dst) <- src (rows, ld_src), zero-filling the pad columns [cols, ld_dst).

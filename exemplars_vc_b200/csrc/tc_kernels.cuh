@@ -73,8 +73,6 @@ struct GemmParams {
   int m_plane_rows, n_plane_rows;
   float* out;    // PARTIAL: [split][t][m] with pitch ld_out;  MU_*: the activations H (T, ld_out)
   int ld_out;
-  __nv_bfloat16* out16;  // PREC_BF16, MU_*: bf16 shadow of H (T, ld_out16), the K operand of the next contraction 1
-  int ld_out16;
   const float* colsum;
   float lam, eps;
   const unsigned char* row_active;
@@ -191,14 +189,20 @@ struct TileCfg {
   static constexpr int kHBufsUsed = kStageQ ? kHBufs / 2 : kHBufs;
   static constexpr int kHBufStride = kStageQ ? 2 * kHBufBytes : kHBufBytes;
   static constexpr int kHBytes = kStageH ? kHBufs * kHBufBytes : 0;
-  static constexpr int kStagesRaw = (kSmemBudget - kHBytes) / kStageBytes;
+  // PREC_BF16: the bf16 shadow of the updated chunk is staged next to it and leaves by TMA too (2-byte per-lane global
+  // stores from the epilogue warps were what bounded the fast mode: profiles/r1_bf16_ncu_summary.txt)
+  static constexpr bool kShadow = kStageH && (kPrec == PREC_BF16);
+  static constexpr int kSBufBytes = kHChunkT * 128 * 2;
+  static constexpr int kSBytes = kShadow ? kHBufs * kSBufBytes : 0;
+  static constexpr int kStagesRaw = (kSmemBudget - kHBytes - kSBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > EVC_MAX_STAGES ? EVC_MAX_STAGES : kStagesRaw;
   static constexpr int kAccCols = kMTiles * kBlockT;
   static constexpr int kAccStages = (512 / kAccCols) >= 2 ? 2 : 1;
   static constexpr int kLoaderWarp = 2 + kEpiWarps;  // H chunk loader, then storer
   static constexpr int kThreads = (kLoaderWarp + (kStageH ? 2 : 0)) * 32;
   static constexpr int kOffH = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kHBytes + 1024;  // + slack to align the ring to 1024 B
+  static constexpr int kOffS = kOffH + kHBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kHBytes + kSBytes + 1024;  // + slack to align the ring to 1024 B
   static constexpr int kRowsPerSub = 128 * kCG;                   // dictionary rows of one MMA (M = 256)
   static_assert(kStages >= 2, "tile does not fit twice in shared memory");
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
@@ -269,7 +273,8 @@ template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, int kEpi, int kP = 
 __global__ void __launch_bounds__(
     (TileCfg<kMTiles, kBlockT, kPrec, kSplitN, kEpi != TEPI_PARTIAL, kEpi == TEPI_MU_FRO>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
-               const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmQ, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmQ,
+               const __grid_constant__ CUtensorMap tmS, const GemmParams p) {
   static_assert(kP == 1 || kP == 2 || kP == 4, "1, 2 or 4 CTA pairs per cluster");
   constexpr bool kFro = (kEpi == TEPI_MU_FRO);
   constexpr bool kStageH = (kEpi != TEPI_PARTIAL);
@@ -305,6 +310,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     tma_prefetch_desc(&tmM);
     tma_prefetch_desc(&tmN);
     if (kStageH) tma_prefetch_desc(&tmH);
+    if (Cfg::kShadow) tma_prefetch_desc(&tmS);
     if (kFro) tma_prefetch_desc(&tmQ);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), Cfg::kFullArrivals);
@@ -495,6 +501,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           mbar_wait(smem_u32(&bar_hready[b]), ph);
           if (!EVC_DBG(p, 16)) {
             tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * Cfg::kHBufStride);
+            if (Cfg::kShadow) tma_store_2d(&tmS, n0, t0 + c * kHChunkT, ring + Cfg::kOffS + b * Cfg::kSBufBytes);
             tma_store_commit();
             tma_store_wait_read();
           }
@@ -579,13 +586,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (tbm + j < p.T && p.row_active[tbm + j]) h[j] = h[j] * quotient(__uint_as_float(v[j]), den, inv_den);
           }
-          if (kBf16 && p.out16 != nullptr && m < p.M_total) {
-            // bf16 shadow of the updated activations: 64 contiguous bytes per warp per frame, straight from registers
-            __nv_bfloat16* o16 = p.out16 + (size_t)tbm * p.ld_out16 + m;
-            const int rows = min(32, p.T - tbm);
+          if (Cfg::kShadow) {
+            // bf16 shadow of the updated activations (the K operand of the next contraction 1), staged like the chunk
+            __nv_bfloat16* sbuf = reinterpret_cast<__nv_bfloat16*>(ring_ptr + Cfg::kOffS + b * Cfg::kSBufBytes) + quarter * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < rows) o16[(size_t)j * p.ld_out16] = __float2bfloat16_rn(h[j]);
+            for (int j = 0; j < 32; ++j) sbuf[j * 128] = __float2bfloat16_rn(h[j]);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) hb[j * 128] = h[j];
@@ -685,15 +690,17 @@ __device__ __forceinline__ void store_r(const ROut& o, int t, int f, float r) {
 // in the workspace -- are staged in shared memory by cp.async.bulk copies issued by one thread and summed from there:
 // with per-lane 16-byte loads this kernel ran at 2.0 TB/s (the SM's outstanding-miss capacity, profiles/r2c_*),
 // bulk copies are not subject to that limit.
-constexpr int kRedCols = 512, kRedMaxBatch = 32;
-__global__ void __launch_bounds__(128)
+// 256 columns x 64 threads per block: 18 KB of staging at the headline shape, so eleven blocks share an SM and the
+// 3 000 blocks of a launch run in under two waves (512 columns: five per SM, 2.7 waves, 17.6 us -- profiles/r2g_*).
+constexpr int kRedCols = 256, kRedThreads = 64, kRedMaxBatch = 32;
+__global__ void __launch_bounds__(kRedThreads)
 reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
                        float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
                        int left_ld, const float* __restrict__ X, int ldx, float eps, ROut ro, int batch) {
   extern __shared__ __align__(128) float red_smem[];  // [batch][kRedCols] staged partials | [n_left][left_rows]
   __shared__ __align__(8) uint64_t bar;
   __shared__ float s_left[8];
-  __shared__ float s_warp[4];
+  __shared__ float s_warp[kRedThreads / 32];
   const int t = blockIdx.x, c0 = blockIdx.y * kRedCols;
   float* stage = red_smem;
   float* lstage = red_smem + (size_t)batch * kRedCols;
@@ -741,7 +748,12 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = a;
         __syncthreads();
-        if (threadIdx.x == 0) s_left[l] = (s_warp[0] + s_warp[1]) + (s_warp[2] + s_warp[3]);
+        if (threadIdx.x == 0) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < kRedThreads / 32; ++w) tot += s_warp[w];
+          s_left[l] = tot;
+        }
         __syncthreads();
       }
     }
@@ -995,7 +1007,7 @@ struct TcLaunch {
     return cache[dev];
   }
   static int launch(const CUtensorMap& tmM, const CUtensorMap& tmN, const CUtensorMap& tmH, const CUtensorMap& tmQ,
-                    const GemmParams& p, cudaStream_t s) {
+                    const CUtensorMap& tmS, const GemmParams& p, cudaStream_t s) {
     auto kern = tc_gemm_kernel<kMTiles, kBlockT, kPrec, kSplitN, kEpi, kP, kShareM>;
     const int nslots = slots();
     if (nslots <= 0) return fail(EVC_ERR_UNSUPPORTED, "clusters of %d CTA pairs cannot be scheduled on this device", kP);
@@ -1020,9 +1032,9 @@ struct TcLaunch {
     static const int dbg = getenv("EVC_DEBUG_FLAGS") ? atoi(getenv("EVC_DEBUG_FLAGS")) : 0;
     GemmParams qp = p;
     qp.debug_flags = dbg;
-    EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, qp));
+    EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, tmS, qp));
 #else
-    EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, p));
+    EVC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmM, tmN, tmH, tmQ, tmS, p));
 #endif
     EVC_LAUNCH_CHECK();
     return EVC_OK;
@@ -1311,7 +1323,7 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
     const CUtensorMap& tmD = (kPrec == PREC_TF32) ? (target ? o.tmBT : o.tmAT)
                              : (kP == 1)          ? (target ? o.tmBT16 : o.tmAT16)
                                                   : (target ? o.tmBT16_s[kP / 4] : o.tmAT16_s[kP / 4]);
-    EVC_TRY((TcLaunch<kC1MTiles, kC1BlockT, kPrec, kSplitN, TEPI_PARTIAL, kP, true>::launch(tmD, tmH, tmH, tmH, p, s)));
+    EVC_TRY((TcLaunch<kC1MTiles, kC1BlockT, kPrec, kSplitN, TEPI_PARTIAL, kP, true>::launch(tmD, tmH, tmH, tmH, tmH, p, s)));
   }
   // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
   const bool from_partials = o.n_left > 0 && !target && o.left_valid;
@@ -1333,7 +1345,7 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
     }
     if (smem > 160 * 1024) return fail(EVC_ERR_UNSUPPORTED, "split-K reduction: %zu bytes of staging exceed shared memory", smem);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(T, ceil_div(cols, kRedCols)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(T, ceil_div(cols, kRedCols)); cfg.blockDim = dim3(kRedThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1395,12 +1407,13 @@ inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR
   }
   // neighbouring CTA pairs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
   p.m_fastest = 1;
-  CUtensorMap tmHc = tmR, tmQc = tmR;  // the fused updates stage H (and the Frobenius numerator) through shared memory
-  if (kPrec == PREC_BF16 && kEpi != TEPI_PARTIAL) { p.out16 = o.h16.as<__nv_bfloat16>(); p.ld_out16 = o.ldN16; }
+  CUtensorMap tmHc = tmR, tmQc = tmR, tmSc = tmR;  // the fused updates stage H (and the Frobenius numerator) through shared memory
+  if (kPrec == PREC_BF16 && kEpi != TEPI_PARTIAL)  // ... and the bf16 shadow of H leaves the same way
+    EVC_TRY(make_tmap_any(&tmSc, o.h16.as<__nv_bfloat16>(), 2, T, o.N, o.ldN16, 128, kHChunkT, false));
   if (kEpi != TEPI_PARTIAL) EVC_TRY(make_tmap(&tmHc, p.out, T, o.N, p.ld_out, 128, kHChunkT, false));
   if (kEpi == TEPI_MU_FRO) EVC_TRY(make_tmap(&tmQc, num0, T, o.N, p.ld_out, 128, kHChunkT, false));
   ProfScope ps(2, s);
-  return Launch::launch(kPrec == PREC_TF32 ? o.tmA : o.tmA16, tmR, tmHc, tmQc, p, s);
+  return Launch::launch(kPrec == PREC_TF32 ? o.tmA : o.tmA16, tmR, tmHc, tmQc, tmSc, p, s);
 }
 
 template <int kEpi>
