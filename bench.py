@@ -426,12 +426,15 @@ def main():
     gc.collect()
     gc.disable()
     if step_resident is not None:
-        for _ in range(args.warmup):
-            step_resident()
-        barrier()
+        # the sampler is started BEFORE the warm-up: spawning nvidia-smi and its first NVML queries stall the driver
+        # for tens of milliseconds (seen as one timed step twice as long as its neighbours), which belongs in the
+        # warm-up, not in the timed region; it keeps sampling every 200 ms through the timed steps
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            step_resident()
+        barrier()
         launches0 = _lib.kernel_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -49,8 +49,9 @@ enum evc_status {
 /* Arithmetic of the two contractions A*H and A^T*R (and of Y = B*H). */
 enum evc_mode {
   EVC_MODE_FP32 = 0,   /* fp32 FFMA on CUDA cores: exact fp32, any shape (also F = 1, the f0 track) */
-  EVC_MODE_3XTF32 = 1, /* fp32-accurate: hi/lo split of both operands in shared memory; hi*hi on tcgen05 kind::tf32,
-                          the two cross terms on kind::f16 (bf16 copies of hi and lo), lo*lo dropped            */
+  EVC_MODE_3XTF32 = 1, /* fp32-accurate: every operand x = x1 + x2 (two bf16 planes, made once where the data is
+                          produced); three tcgen05 kind::f16 MMAs per product (x2*y1 + x1*y2 + x1*y1), fp32
+                          accumulate in TMEM.  (The enumerator keeps its round-1 name for ABI stability.)       */
   EVC_MODE_TF32 = 2,   /* tcgen05 kind::tf32, one MMA per product: fast mode                           */
   EVC_MODE_BF16 = 3    /* tcgen05 kind::f16 on bf16 copies of A, of the ratio and of H (shadow kept by the fused
                           update), fp32 accumulate and fp32 multiplicative update: fastest, ~1e-3 on H     */
@@ -106,6 +107,8 @@ void evc_default_params(evc_solve_params* p);
 int evc_dict_create(const float* A, int ldA, const float* B, int ldB, int F, int N, int mode,
                     void* stream, evc_dict_t* out);
 int evc_dict_destroy(evc_dict_t d);
+/* `mode` reports the mode that RUNS: a problem below one MMA operand tile (F < 64 or N < 128, e.g. the F = 1 f0 track
+ * of 04_align_n_nmf.py:288) runs on the exact-fp32 CUDA-core kernels whatever tensor-core mode was asked for. */
 int evc_dict_info(evc_dict_t d, int* F, int* N, int* mode, int* has_target);
 /* Copy A^T 1 (N floats) to a device buffer. */
 int evc_dict_colsum(evc_dict_t d, float* out, void* stream);
