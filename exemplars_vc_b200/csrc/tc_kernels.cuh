@@ -282,7 +282,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   constexpr int kHB = Cfg::kHBufsUsed;  // chunk buffers in use
   constexpr int kStages = Cfg::kStages;
   constexpr int kAccStages = Cfg::kAccStages;
-  constexpr bool kBf16 = (kPrec == PREC_BF16);
   constexpr uint32_t kFmt = (kPrec == PREC_TF32) ? kFmtTF32 : kFmtBF16;
   constexpr uint32_t kIdesc = make_idesc(kFmt, 128 * kCG, kBlockT);
 
