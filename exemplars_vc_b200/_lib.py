@@ -72,6 +72,7 @@ def lib():
     L.evc_griffin_lim.argtypes = [vp, ip, ip, ip, ip, ip, vp, vp, vp, vp, vp]
     L.evc_stft.argtypes = [vp, C.c_longlong, ip, ip, vp, vp, vp]
     L.evc_istft.argtypes = [vp, ip, ip, ip, vp, vp, vp]
+    L.evc_dtw.argtypes = [vp, vp, vp, vp, ip, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp]
     L.evc_gather_stack.argtypes = [vp, ip, ip, ip, vp, vp, vp, ip, ip, vp, ip, vp]
     L.evc_profile_enable.argtypes = [vp, ip]
     L.evc_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(ip)]
@@ -84,7 +85,7 @@ def lib():
     L.evc_p2p_detach.argtypes = [vp]
     for name in ("evc_dict_create", "evc_dict_destroy", "evc_dict_info", "evc_dict_colsum", "evc_solve",
                  "evc_solve_batched", "evc_convert", "evc_reconstruct", "evc_objective", "evc_factorize_convert_host",
-                 "evc_gather_stack", "evc_residual", "evc_convert_residual", "evc_griffin_lim", "evc_stft",
+                 "evc_gather_stack", "evc_dtw", "evc_residual", "evc_convert_residual", "evc_griffin_lim", "evc_stft",
                  "evc_istft", "evc_profile_enable", "evc_profile_read", "evc_comm_unique_id", "evc_comm_create", "evc_comm_destroy", "evc_dict_attach_comm", "evc_p2p_alloc",
                  "evc_p2p_attach", "evc_p2p_detach"):
         getattr(L, name).restype = ip

@@ -12,6 +12,7 @@
 #include "nccl_shim.cuh"
 #include "p2p_allreduce.cuh"
 #include "audio_kernels.cuh"
+#include "dtw_kernels.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -545,6 +546,30 @@ int evc_griffin_lim(const float* mag, int ldm, int T, int fft_size, int hop, int
   }();
   cudaFreeAsync(frames, s); cudaFreeAsync(xa, s); cudaFreeAsync(xb, s);
   return st;
+}
+
+int evc_dtw(const double* A, const long long* a_off, const double* B, const long long* b_off, int n_files, int dim,
+            int max_frames, unsigned char* dirs, const long long* dir_off, int* path_a, int* path_b,
+            const long long* path_off, int* path_len, double* dist, void* stream) {
+  if (!A || !a_off || !B || !b_off || !dirs || !dir_off || !path_a || !path_b || !path_off || !path_len || !dist ||
+      n_files < 0 || dim < 1 || max_frames < 1)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "evc_dtw: bad argument");
+  if (n_files == 0) return EVC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = (size_t)3 * max_frames * sizeof(double);
+  if (smem > 200 * 1024) return fail(EVC_ERR_UNSUPPORTED, "evc_dtw: files longer than %d frames are not supported", (int)(200 * 1024 / 24));
+  static bool configured[64] = {false};
+  int dev = 0;
+  EVC_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    EVC_CUDA(cudaFuncSetAttribute(dtw::forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  dtw::forward_kernel<<<n_files, dtw::kThreads, smem, s>>>(A, a_off, B, b_off, dim, dirs, dir_off, dist, max_frames);
+  EVC_LAUNCH_CHECK();
+  dtw::traceback_kernel<<<ceil_div(n_files, 64), 64, 0, s>>>(a_off, b_off, dirs, dir_off, path_a, path_b, path_off, path_len, n_files);
+  EVC_LAUNCH_CHECK();
+  return EVC_OK;
 }
 
 int evc_objective(evc_dict_t d, const float* X, int ldX, int T, const float* H, int ldH, int loss, float epsilon,

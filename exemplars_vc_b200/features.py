@@ -92,3 +92,48 @@ def build_dictionaries(src_files: Sequence, tar_files: Sequence, src_paths: Sequ
     A = side(S, src_paths)
     B = side(Tg, tar_paths)
     return ExemplarDictionary(A, B, mode=mode)
+
+
+def dtw_alignment(feat_full_A: Sequence, feat_full_B: Sequence):
+    """DTW index paths of parallel utterances: drop-in for ``01_make_dict_parallel.dtw_alignment`` (:239-249), which
+    runs ``dtw(feat_A.T, feat_B.T, lambda x, y: sum(np.square(x - y)))`` (:226) per file pair in a process pool.
+
+    feat_full_A[i], feat_full_B[i] : (order, n_frames) feature matrices of file i, the reference's layout (:219-220)
+    returns (dtw_paths, None, None) like the reference; dtw_paths[i] = (p, q): equal-length int arrays,
+    exemplar k of file i pairs frame p[k] of A with frame q[k] of B (what make_exemplar_dict_* index with, :205-206).
+    All file pairs are aligned by one launch (one block per pair, float64, bit-identical to the package's recursion)."""
+    dev = _device()
+    if len(feat_full_A) != len(feat_full_B):
+        raise ValueError("feat_full_A and feat_full_B must hold the same number of files")
+    n = len(feat_full_A)
+    if n == 0:
+        return [], None, None
+    fa = [np.ascontiguousarray(np.asarray(a, dtype=np.float64).T) for a in feat_full_A]      # (frames, order)
+    fb = [np.ascontiguousarray(np.asarray(b, dtype=np.float64).T) for b in feat_full_B]
+    dim = fa[0].shape[1]
+    if any(m.ndim != 2 or m.shape[1] != dim for m in fa + fb):
+        raise ValueError("every file must be a 2-D (order, n_frames) matrix of the same order")
+    ra, cb = np.array([len(m) for m in fa], np.int64), np.array([len(m) for m in fb], np.int64)
+    if (ra < 1).any() or (cb < 1).any():
+        raise ValueError("every file needs at least one frame")
+    a_off, b_off = np.concatenate([[0], np.cumsum(ra)]), np.concatenate([[0], np.cumsum(cb)])
+    dir_off = np.concatenate([[0], np.cumsum(ra * cb)])
+    path_off = np.concatenate([[0], np.cumsum(ra + cb)])
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)    # noqa: E731
+    A, B = t(np.concatenate(fa), torch.float64), t(np.concatenate(fb), torch.float64)
+    a_o, b_o, d_o, p_o = (t(x, torch.int64) for x in (a_off, b_off, dir_off, path_off))
+    dirs = torch.empty(int(dir_off[-1]), dtype=torch.uint8, device=dev)
+    pa = torch.empty(int(path_off[-1]), dtype=torch.int32, device=dev)
+    pb = torch.empty_like(pa)
+    plen = torch.empty(n, dtype=torch.int32, device=dev)
+    dist = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().evc_dtw(_ptr(A), _ptr(a_o), _ptr(B), _ptr(b_o), n, dim, int(max(ra.max(), 1)), _ptr(dirs),
+                                      _ptr(d_o), _ptr(pa), _ptr(pb), _ptr(p_o), _ptr(plen), _ptr(dist), _stream(dev)))
+    pa_h, pb_h, len_h = pa.cpu().numpy(), pb.cpu().numpy(), plen.cpu().numpy()
+    paths = []
+    for i in range(n):
+        s0, L = int(path_off[i]), int(len_h[i])
+        paths.append((pa_h[s0:s0 + L][::-1].astype(np.int64), pb_h[s0:s0 + L][::-1].astype(np.int64)))
+    dtw_alignment.last_distances = dist.cpu().numpy()
+    return paths, None, None

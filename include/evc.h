@@ -197,6 +197,19 @@ int evc_stft(const double* x, long long len, int fft_size, int hop, const double
 int evc_istft(const double* spec, int T, int fft_size, int hop, const double* window, double* x_out, void* stream);
 
 /*
+ * DTW alignment of n_files parallel utterance pairs (01_make_dict_parallel.py:215-249: the `dtw`
+ * package with the squared-L2 local cost of :226, default step pattern).  Device pointers.  A (sum_r, dim) and
+ * B (sum_c, dim) hold the per-file feature frames (float64, row-major) back to back; file f owns rows
+ * [a_off[f], a_off[f+1]) / [b_off[f], b_off[f+1]) (n_files + 1 offsets each); max_frames >= every file's frame count
+ * on the A side.  dirs = workspace of sum_f r_f * c_f bytes, file f at dir_off[f].  Outputs: the alignment path of
+ * file f, REVERSED (from (r-1, c-1) back to (0, 0)), in path_a / path_b[path_off[f] ...] (room for r_f + c_f - 1
+ * entries), its length in path_len[f], and dist[f] = accumulated cost / (r + c) as the package returns it.
+ */
+int evc_dtw(const double* A, const long long* a_off, const double* B, const long long* b_off, int n_files, int dim,
+            int max_frames, unsigned char* dirs, const long long* dir_off, int* path_a, int* path_b,
+            const long long* path_off, int* path_len, double* dist, void* stream);
+
+/*
  * Optional: replace the NCCL all-reduce of the exemplar-sharded path by libevc_b200's own kernel over NVLink peer
  * memory (one node, 2..8 ranks, one process per GPU).  Every rank calls evc_p2p_alloc (allocates the exchange buffer
  * for up to max_frames frames and returns a 64-byte CUDA IPC handle), the handles of all ranks are exchanged by the

@@ -171,3 +171,53 @@ def test_dictionary_cache_reuses_and_never_goes_stale():
     W3_ref, _, _ = o.kl_mu(X, A, tol=0, max_iter=20)
     assert rel_fro(W3, W3_ref) < 1e-3 and rel_fro(W3, W1) > 1e-2
     dictionary_cache.clear()
+
+
+def test_dtw_alignment_on_the_device_matches_the_oracle():
+    """features.dtw_alignment (drop-in for 01_make_dict_parallel.dtw_alignment, :239-249): ragged files, the
+    reference's (order, n_frames) layout, paths and distances bit-identical to the restated `dtw` recursion."""
+    from exemplars_vc_b200 import features
+    from oracle import dtw_oracle as o
+    rng = np.random.default_rng(31)
+    lens = [(37, 41), (1, 9), (64, 64), (120, 77), (5, 1)]
+    A = [np.cumsum(rng.standard_normal((24, r)), axis=1) for r, _ in lens]        # (order, n_frames)
+    B = [np.cumsum(rng.standard_normal((24, c)), axis=1) for _, c in lens]
+    A[2] = B[2].copy()                                                              # identical pair: pure diagonal, all ties
+    paths, none1, none2 = features.dtw_alignment(A, B)
+    assert none1 is None and none2 is None and len(paths) == len(lens)
+    for i, (a, b) in enumerate(zip(A, B)):
+        dist, _, _, (p, q) = o.dtw(a.T, b.T)
+        assert np.array_equal(paths[i][0], p) and np.array_equal(paths[i][1], q), i
+        assert features.dtw_alignment.last_distances[i] == dist
+    assert np.array_equal(paths[2][0], np.arange(64)) and np.array_equal(paths[2][1], np.arange(64))
+    # the paths index the per-file features exactly as make_exemplar_dict does (:205-206) and feed build_dictionaries
+    src = [np.abs(a.T).astype(np.float32) for a in A]
+    tar = [np.abs(b.T).astype(np.float32) for b in B]
+    d = features.build_dictionaries(src, tar, [p for p, _ in paths], [q for _, q in paths], mode="fp32")
+    assert d.N == sum(len(p) for p, _ in paths)
+    d.close()
+    with pytest.raises(ValueError):
+        features.dtw_alignment(A, B[:-1])
+
+
+def test_dtw_alignment_at_utterance_length():
+    """Two ~7 s utterances at a 5 ms hop (1 400 frames, 25 coefficients), the largest files the reference ships."""
+    from exemplars_vc_b200 import features
+    from oracle import dtw_oracle as o
+    rng = np.random.default_rng(32)
+    a = np.cumsum(rng.standard_normal((25, 1380)), axis=1)
+    warp = np.clip(np.arange(1290) * 1380 // 1290 + rng.integers(-3, 4, 1290), 0, 1379)
+    b = a[:, np.sort(warp)] + 0.05 * rng.standard_normal((25, 1290))
+    (p, q), = features.dtw_alignment([a], [b])[0]
+    C = o.local_cost(a.T, b.T)
+    # the accumulated cost along the device path equals the optimum of a vectorised numpy recursion
+    D = np.full((1381, 1291), np.inf)
+    D[0, 0] = 0.0
+    for i in range(1, 1381):
+        row = D[i]
+        up_diag = np.minimum(D[i - 1, 1:], D[i - 1, :-1])
+        for j in range(1, 1291):
+            row[j] = C[i - 1, j - 1] + min(up_diag[j - 1], row[j - 1])
+    assert (p[0], q[0], p[-1], q[-1]) == (0, 0, 1379, 1289)
+    assert np.isclose(C[p, q].sum(), D[-1, -1], rtol=1e-12)
+    assert features.dtw_alignment.last_distances[0] == pytest.approx(D[-1, -1] / (1380 + 1290), rel=1e-12)

@@ -139,3 +139,39 @@ def test_griffin_lim_oracle_is_bit_identical_to_the_reference_functions():
     for it in (1, 3, 30):
         x = g.reconstruct_signal_griffin_lim(z["mag"].astype(np.float64), fft, hop, it, z["x0"])
         assert np.array_equal(x, z["x%d" % it])
+
+
+def test_dtw_oracle_properties_and_known_answer():
+    """oracle/dtw_oracle.py (restatement of the un-vendored `dtw` package's recursion, parity unpinned -- see its
+    header): endpoints, monotone unit steps, optimality against brute force on a tiny case, the hand-checkable
+    known answer of two shifted ramps, and the first-minimum tie-break (diagonal, then up, then left)."""
+    import itertools
+    from oracle import dtw_oracle as d
+    rng = np.random.default_rng(2)
+    x, y = rng.standard_normal((7, 3)), rng.standard_normal((5, 3))
+    dist, C, D1, (p, q) = d.dtw(x, y)
+    assert (p[0], q[0]) == (0, 0) and (p[-1], q[-1]) == (6, 4) and len(p) == len(q)
+    steps = set(zip(np.diff(p).tolist(), np.diff(q).tolist()))
+    assert steps <= {(1, 1), (1, 0), (0, 1)}
+    assert np.isclose(C[p, q].sum(), D1[-1, -1]) and np.isclose(dist, D1[-1, -1] / 12)
+    assert np.array_equal(C, np.array([[sum(np.square(a - b)) for b in y] for a in x]))      # the lambda of :226, bit for bit
+    # brute force over all monotone paths of a 4 x 3 problem
+    x, y = rng.standard_normal((4, 2)), rng.standard_normal((3, 2))
+    _, C, D1, _ = d.dtw(x, y)
+
+    def best(i, j):
+        if i == 0 and j == 0:
+            return C[0, 0]
+        cands = []
+        if i > 0 and j > 0: cands.append(best(i - 1, j - 1))
+        if i > 0: cands.append(best(i - 1, j))
+        if j > 0: cands.append(best(i, j - 1))
+        return C[i, j] + min(cands)
+    assert np.isclose(D1[-1, -1], best(3, 2))
+    # y = x with its first frame held twice more: the zero-cost path waits on x[0], then runs along the diagonal
+    ramp = np.arange(6, dtype=float)[:, None]
+    dist, _, _, (p, q) = d.dtw(ramp, np.concatenate([np.zeros((2, 1)), ramp]))
+    assert dist == 0.0 and np.array_equal(p, [0, 0, 0, 1, 2, 3, 4, 5]) and np.array_equal(q, np.arange(8))
+    # ties: identical constant sequences -> every step is the diagonal (first minimum)
+    _, _, _, (p, q) = d.dtw(np.ones((4, 2)), np.ones((4, 2)))
+    assert np.array_equal(p, np.arange(4)) and np.array_equal(q, np.arange(4))
