@@ -367,8 +367,12 @@ class DictionaryCache:
         total = int(flat[:n8].view(np.uint64).sum(dtype=np.uint64)) if n8 else 0
         return (total + int(flat[n8:].sum(dtype=np.uint64)) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
-    def get(self, A: np.ndarray, B: Optional[np.ndarray], mode: str) -> "ExemplarDictionary":
+    def get(self, A: np.ndarray, B: Optional[np.ndarray], mode: str, validate=None) -> "ExemplarDictionary":
+        """`validate` (optional callable) runs before a dictionary is BUILT -- a hit was validated when it was built and
+        its content is unchanged, so the 40 MB finiteness scan of the reference's check_array is not repeated."""
         if not torch.cuda.is_available():
+            if validate is not None:
+                validate()          # input errors are reported as such even where nothing can run
             raise RuntimeError("exemplars_vc_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         key = (self._ident(A), self._ident(B), mode, torch.cuda.current_device())
         sa = self._checksum(A)
@@ -378,6 +382,8 @@ class DictionaryCache:
             self._entries[key] = self._entries.pop(key)     # most recently used last
             self.hits += 1
             return hit[0]
+        if validate is not None:
+            validate()
         if hit is not None:
             self._entries.pop(key)[0].close()
         self.misses += 1

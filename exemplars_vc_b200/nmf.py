@@ -83,11 +83,16 @@ def non_negative_factorization(X, W=None, H=None, n_components="auto", *, init=N
     H_arr = np.asarray(H)
     # sklearn check_array(force_all_finite=True) runs before the sign check (NaN < 0 is False, so a NaN would
     # otherwise slip through): same exception type and wording
-    for name, arr in (("X", X_in), ("H", H_arr)):
+    def _check_finite(name, arr):
         if arr.dtype.kind == "f" and arr.size and not np.isfinite(arr).all():
             if np.isnan(arr).any():
                 raise ValueError("Input %s contains NaN." % name)
             raise ValueError("Input %s contains infinity or a value too large for %r." % (name, arr.dtype))
+
+    _check_finite("X", X_in)
+    use_cache = dictionary is None and cache_dictionaries
+    if not use_cache and dictionary is None:
+        _check_finite("H", H_arr)          # (a cached dictionary was scanned when it was built; see DictionaryCache.get)
     if X_in.size and X_in.min() < 0:
         raise ValueError("Negative values in data passed to NMF (input X)")
     _check_dictionary_dtype(X_in, H_arr)
@@ -111,7 +116,8 @@ def non_negative_factorization(X, W=None, H=None, n_components="auto", *, init=N
     # the dictionary stays resident across calls with the same (unchanged) array: dictionary.DictionaryCache
     own = dictionary is None and not cache_dictionaries
     d = dictionary if dictionary is not None else (
-        ExemplarDictionary(H_arr, None, mode=mode) if own else dictionary_cache.get(H_arr, None, mode))
+        ExemplarDictionary(H_arr, None, mode=mode) if own
+        else dictionary_cache.get(H_arr, None, mode, validate=lambda: _check_finite("H", H_arr)))
     try:
         t0 = time.time()
         act = d.solve(X_in, beta_loss=beta, tol=tol, max_iter=max_iter, lam=lam, lambda_step=lam_step)

@@ -42,6 +42,18 @@ def test_shape_and_sign_errors():
         nmf.non_negative_factorization(Xn, H=A, init="custom", update_H=False, solver="mu")
 
 
+def test_non_finite_inputs_raise_like_check_array():
+    """sklearn's check_array rejects NaN / inf before anything else (a NaN is not < 0, so the sign check alone
+    would let it through)."""
+    X, A = _xa()
+    Xn = X.copy(); Xn[1, 2] = np.nan
+    with pytest.raises(ValueError, match="Input X contains NaN"):
+        nmf.non_negative_factorization(Xn, H=A, init="custom", update_H=False, solver="mu")
+    An = A.copy(); An[0, 0] = np.inf
+    with pytest.raises(ValueError, match="Input H contains infinity"):
+        nmf.non_negative_factorization(X, H=An, init="custom", update_H=False, solver="mu")
+
+
 def test_no_cpu_fallback_without_a_gpu():
     import torch
     if torch.cuda.is_available():
