@@ -229,10 +229,10 @@ double evc_last_enqueue_ms(void);
 /* Diagnostics: number of kernels this library has launched in this process. */
 long long evc_kernel_launch_count(void);
 
-/* Diagnostics: tensor-core passes one logical product costs in `mode`, in units of a dense MMA pass of the mode's
- * roofline type: EVC_MODE_3XTF32 -> 2 (TF32 hi*hi + two BF16 cross-term MMAs, each worth half a TF32 pass; 3 when
- * EVC_SPLIT_CROSS16=0 selects three TF32 MMAs), EVC_MODE_TF32 / EVC_MODE_BF16 -> 1, EVC_MODE_FP32 -> 0 (no tensor
- * cores).  bench.py multiplies the algorithmic TFLOP/s by this to get the executed figure ncu's tensor pipe sees. */
+/* Diagnostics: MMAs one logical product costs in `mode`: EVC_MODE_3XTF32 -> 3 (bf16 MMAs: x2*y1 + x1*y2 + x1*y1),
+ * EVC_MODE_TF32 -> 1 (a tf32 MMA), EVC_MODE_BF16 -> 1 (a bf16 MMA), EVC_MODE_FP32 -> 0 (no tensor cores).  bench.py
+ * multiplies the algorithmic TFLOP/s by this to get the executed figure ncu's tensor pipe sees (against the dense
+ * BF16 rate for the first and third mode, the dense TF32 rate for the second). */
 int evc_mma_passes_per_product(int mode);
 
 /*

@@ -1,6 +1,5 @@
 """Measured parity per arithmetic mode (not a test): relative Frobenius error of H and Y and relative error of the
-objective against the reference's float64 goldens.  Usage: python tests/manual/accuracy_modes.py [modes...]
-(EVC_SPLIT_CROSS16=0 selects the classic three-TF32-MMA split for the "3xtf32" mode)."""
+objective against the reference's float64 goldens.  Usage: python tests/manual/accuracy_modes.py [modes...]"""
 import os
 import sys
 
@@ -17,7 +16,6 @@ CASES = ["kl_13x32x8_tol1e-4", "kl_201x777x37_tol1e-4", "kl_513x2000x64_tol1e-4"
 
 def main():
     modes = sys.argv[1:] or ["fp32", "3xtf32", "tf32", "bf16"]
-    print("EVC_SPLIT_CROSS16 =", os.environ.get("EVC_SPLIT_CROSS16", "(default)"))
     for name in CASES:
         g = load_golden(name)
         X, A, B = (g["X"], g["A"], g["B"]) if name.startswith("speech") else golden_inputs(g)
