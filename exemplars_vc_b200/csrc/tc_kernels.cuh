@@ -207,7 +207,6 @@ struct TileCfg {
   static_assert(kStages >= 2, "tile does not fit twice in shared memory");
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
   static_assert(kBlockT % 32 == 0 && kBlockT >= 32 && kBlockT <= 256, "bad frame tile");
-  static_assert(!kStageH || kMTiles == 1, "H staging assumes one sub-tile per work item");
   static_assert(!kSplitN || kPrec == PREC_SPLIT, "only the split mode derives planes in shared memory");
   static_assert(!kSplitN || kAccStages == 1, "the epilogue warps split during the main loop: one accumulator stage");
   static_assert(!kSplitN || (kNRows * 4) % (kEpiWarps * 32) == 0, "every split thread gets whole units");
@@ -347,6 +346,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     }
     return w;
   };
+  // dictionary sub-tiles of row group g that hold at least one real row (the others are pure padding: no MMAs, no update)
+  auto valid_subtiles = [&](int g) {
+    const int rows_left = p.M_total - g * (Cfg::kRowsPerSub * kMTiles);
+    return max(0, min(kMTiles, (rows_left + Cfg::kRowsPerSub - 1) / Cfg::kRowsPerSub));
+  };
   // the pair leader's "full" barriers as shared::cluster addresses (stage i at + 8 i); == local address & ~(1 << 24)
   const uint32_t full_leader = mapa_rank(smem_u32(&bar_full[0]), leader);
   // cluster ranks of the CTAs that hold the same half of the shared operand tile as this one; all CTAs; this pair
@@ -470,10 +474,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       int hbase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = item_of(item);
-        const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
+        const int t0 = w.t_tile * kBlockT + w.t_off;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
-        for (int c = 0; c < nch; ++c) {
-          const int seq = hbase + c, b = seq % kHB;
+        const int nsub = valid_subtiles(w.m_group);
+        // chunk cc of the item = chunk cc % nch of dictionary sub-tile cc / nch
+        for (int cc = 0; cc < nsub * nch; ++cc) {
+          const int i = cc / nch, c = cc - i * nch;
+          const int n0 = (w.m_group * kMTiles + i) * Cfg::kRowsPerSub + (int)rank * 128;
+          const int seq = hbase + cc, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hempty[b]), ph ^ 1u);
           const uint32_t full = smem_u32(&bar_hfull[b]);
@@ -483,7 +491,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           if (kFro)
             tma_load_2d(ring + Cfg::kOffH + b * Cfg::kHBufStride + kHBufBytes, &tmQ, n0, t0 + c * kHChunkT, full, kEvictFirst);
         }
-        hbase += nch;
+        hbase += nsub * nch;
       }
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp + 1) {
@@ -492,10 +500,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       int hbase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = item_of(item);
-        const int t0 = w.t_tile * kBlockT + w.t_off, n0 = w.m_group * Cfg::kRowsPerSub + (int)rank * 128;
+        const int t0 = w.t_tile * kBlockT + w.t_off;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
-        for (int c = 0; c < nch; ++c) {
-          const int seq = hbase + c, b = seq % kHB;
+        const int nsub = valid_subtiles(w.m_group);
+        for (int cc = 0; cc < nsub * nch; ++cc) {
+          const int i = cc / nch, c = cc - i * nch;
+          const int n0 = (w.m_group * kMTiles + i) * Cfg::kRowsPerSub + (int)rank * 128;
+          const int seq = hbase + cc, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           mbar_wait(smem_u32(&bar_hready[b]), ph);
           if (!EVC_DBG(p, 16)) {
@@ -506,7 +517,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           }
           mbar_arrive(smem_u32(&bar_hempty[b]));
         }
-        hbase += nch;
+        hbase += nsub * nch;
       }
       tma_store_wait_all();
     }
@@ -542,21 +553,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
       tc_fence_after();
       if (kStageH) {
         // ---- fused multiplicative update through the shared-memory H chunks ----
-        const int m = m_group * Cfg::kRowsPerSub + (int)rank * 128 + quarter * 32 + lane;
-        float den = ((m < p.M_total && !kFro) ? p.colsum[m] : 1.f) + p.lam;
-        if (den == 0.f) den = p.eps;
-        const float inv_den = __frcp_rn(den);
-        // this lane's entries of the leftover dictionary rows (n_left <= 8)
-        float la[8];
-#pragma unroll
-        for (int l = 0; l < 8; ++l) la[l] = (l < p.n_left && m < p.M_total) ? p.left_a[(size_t)l * p.left_lda + m] : 0.f;
         const int nch = max(0, min(w.t_cols / kHChunkT, (p.T - t0 + kHChunkT - 1) / kHChunkT));
-        for (int c = half; c < nch; c += 2) {
-          const int seq = hbase + c, b = seq % kHB;
+        const int nsub = valid_subtiles(m_group);
+        int cur_i = -1, m = 0;
+        float den = 1.f, inv_den = 1.f;
+        float la[8];  // this lane's entries of the leftover dictionary rows (n_left <= 8)
+        for (int cc = half; cc < nsub * nch; cc += 2) {
+          const int i = cc / nch, c = cc - i * nch;
+          if (i != cur_i) {  // per dictionary sub-tile: this lane's row, its denominator, its leftover entries
+            cur_i = i;
+            m = (m_group * kMTiles + i) * Cfg::kRowsPerSub + (int)rank * 128 + quarter * 32 + lane;
+            den = ((m < p.M_total && !kFro) ? p.colsum[m] : 1.f) + p.lam;
+            if (den == 0.f) den = p.eps;
+            inv_den = __frcp_rn(den);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) la[l] = (l < p.n_left && m < p.M_total) ? p.left_a[(size_t)l * p.left_lda + m] : 0.f;
+          }
+          const int seq = hbase + cc, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
           uint32_t v[32];
           if (!EVC_DBG(p, 64))
-            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kBlockT + c * 32), v);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * kMTiles + i) * kBlockT + c * 32), v);
           mbar_wait(smem_u32(&bar_hfull[b]), ph);
           float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * Cfg::kHBufStride) + quarter * 32 + lane;
           float h[32];
@@ -605,11 +622,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) sv[j] = h[j] * a;
             const float tot = warp_transpose_sum(sv, lane);
-            const int prow = (m_group * kCG + (int)rank) * 4 + quarter;  // one partial row per 32 exemplars
+            const int prow = ((m_group * kMTiles + i) * kCG + (int)rank) * 4 + quarter;  // one partial row per 32 exemplars
             p.left_out[((size_t)l * p.left_ld + (t0 + c * 32 + lane)) * p.left_rows + prow] = tot;
           }
         }
-        hbase += nch;
+        hbase += nsub * nch;
       }
 #pragma unroll
       for (int i = 0; i < (kStageH ? 0 : kMTiles); ++i) {
@@ -1214,6 +1231,14 @@ inline int c1_pairs(int mode) {
   if (mode != EVC_MODE_3XTF32 || want == 1) return 1;
   return c1_slots_for(want) > 0 ? want : 1;  // a device that cannot co-schedule such clusters runs plain pairs
 }
+#ifndef EVC_C2_MTILES_DEFAULT
+#define EVC_C2_MTILES_DEFAULT 1
+#endif
+// dictionary sub-tiles per work item of contraction 2 (fp32-accurate mode, plain pairs): EVC_C2_MTILES = 1 | 2
+inline int c2_mtiles() {
+  static const int v = getenv("EVC_C2_MTILES") ? atoi(getenv("EVC_C2_MTILES")) : EVC_C2_MTILES_DEFAULT;
+  return v == 2 ? 2 : 1;
+}
 inline int c2_slots_for(int P) {
   if (P == 2) return TcLaunch<kC2MTiles, kC2BlockT, PREC_SPLIT, false, TEPI_MU_KL, 2, false>::slots();
   if (P == 4) return TcLaunch<kC2MTiles, kC2BlockT, PREC_SPLIT, false, TEPI_MU_KL, 4, false>::slots();
@@ -1379,12 +1404,16 @@ inline int contract_wh(DictOperands& o, int mode, const float* H, int ldH, int T
 
 // Second contraction with a fused epilogue.  `R` is what multiplies A^T: the ratio (KL) or A H (Frobenius); in the
 // split / bf16 modes it lives in o.r16 (made by the reduction / ratio kernels).
-template <int kPrec, int kEpi, int kP = 1>
+// kMT = dictionary sub-tiles (of 256 exemplars) per work item.  kMT = 2 makes an item 512 exemplars x 256 frames: the
+// two sub-tiles share every K-block of the ratio tile, so a pair ingests 3 operand tiles per 2 products instead of
+// 4 (both GEMMs are bound by what an SM can ingest) -- at the price of all of TMEM for one item, i.e.
+// no overlap of the fused update with the next item's MMAs.
+template <int kPrec, int kEpi, int kP = 1, int kMT = kC2MTiles>
 inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR, GemmParams p, const float* num0,
                        cudaStream_t s) {
-  using Launch = TcLaunch<kC2MTiles, kC2BlockT, kPrec, false, kEpi, kP, false>;
+  using Launch = TcLaunch<kMT, kC2BlockT, kPrec, false, kEpi, kP, false>;
   if (kP > 1 && Launch::slots() <= 0)  // this device cannot co-schedule such clusters: plain pairs
-    return contract2_p<kPrec, kEpi, 1>(o, mode, T, R, ldR, p, num0, s);
+    return contract2_p<kPrec, kEpi, 1, kMT>(o, mode, T, R, ldR, p, num0, s);
   const int bke = bk_elems(mode);
   const int planes = (kPrec == PREC_SPLIT) ? 2 : 1;
   CUtensorMap tmR;
@@ -1394,7 +1423,7 @@ inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR
                            o.ldA16, bke, kC2BlockT / kCG / kP));
   p.M_total = o.N; p.T = T; p.K = o.F;
   // row groups of 256 exemplars, dealt to the pairs of a cluster in runs of kP: the work items are cluster-level
-  p.num_m_groups = ceil_div(ceil_div(o.N, 128 * kC2MTiles * kCG), kP); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
+  p.num_m_groups = ceil_div(ceil_div(o.N, 128 * kMT * kCG), kP); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(o.F, bke); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
   p.m_plane_rows = (int)o.a_rows; p.n_plane_rows = (int)o.r_rows;
@@ -1422,6 +1451,7 @@ inline int contract2_t(DictOperands& o, int mode, int T, const float* R, int ldR
     const int P = c2_pairs(mode);
     if (P == 2) return contract2_p<PREC_SPLIT, kEpi, 2>(o, mode, T, R, ldR, p, num0, s);
     if (P == 4) return contract2_p<PREC_SPLIT, kEpi, 4>(o, mode, T, R, ldR, p, num0, s);
+    if (c2_mtiles() == 2) return contract2_p<PREC_SPLIT, kEpi, 1, 2>(o, mode, T, R, ldR, p, num0, s);
     return contract2_p<PREC_SPLIT, kEpi>(o, mode, T, R, ldR, p, num0, s);
   }
   if (mode == EVC_MODE_BF16) return contract2_p<PREC_BF16, kEpi>(o, mode, T, R, ldR, p, num0, s);
