@@ -98,12 +98,23 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
-    def start(self):
+    def start(self, wait_first_sample_s: float = 3.0):
+        """Starts the sampler and waits until its FIRST sample is on disk: loading NVML and the first query stall the
+        driver for tens of milliseconds, which must not land in a timed region (the periodic samples after it do not)."""
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < wait_first_sample_s:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
