@@ -326,6 +326,15 @@ class ExemplarDictionary:
         """Device tensor -> numpy (the D2H leg of the end-to-end path).  With ``key`` the copy lands in a
         cached pinned buffer that the NEXT call with the same key overwrites; without, a fresh array."""
         if key is None:
+            if t.numel() * 4 >= (8 << 20):
+                # large results (the 57-80 MB activation matrix) land in page-locked memory that the returned array
+                # owns: a pageable D2H copy runs at a quarter of the PCIe rate, and when the array comes back as an
+                # input (convert(H)) the upload is fast too.  torch's host allocator recycles the block once the
+                # caller drops the array.
+                buf = torch.empty(tuple(t.shape), dtype=torch.float32, pin_memory=True)
+                buf.copy_(t.detach(), non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return buf.numpy()
             return t.detach().to("cpu", torch.float32).contiguous().numpy()
         shape = tuple(t.shape)
         buf = self._pinned.get(key)
