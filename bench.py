@@ -461,8 +461,13 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
 
     # ---- end to end through the public API, host buffers
-    for _ in range(1 if step_resident is not None else max(args.warmup, 1)):
-        step_e2e()
+    # warm-up of the end-to-end loop: at least two steps whose results are HELD exactly like the timed ones, so that
+    # the second buffer each step needs while the previous step's result is still referenced (80 MB of H on the
+    # device, a page-locked host block for the script-level path) is allocated here and not in the timed region
+    # (seen as a second timed step 60 ms longer than its neighbours)
+    act_e = yh = hh = None
+    for _ in range(2 if step_resident is not None else max(args.warmup, 2)):
+        act_e, yh, hh = step_e2e()
     barrier()
     if step_resident is None:
         sampler = ClockSampler(local_rank)
