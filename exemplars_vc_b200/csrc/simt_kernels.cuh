@@ -201,7 +201,7 @@ __global__ void ratio_kernel(const float* __restrict__ X, int ldx, const float* 
 // (sklearn forms sum_all WH as dot(W.sum(0), A.sum(1)); it is the same number up to rounding.)
 // loss == FROBENIUS: sum (X - WH)^2.
 // Four warps per frame (a double-precision log per element: with one warp per frame a 513-bin frame was a serial
-// chain of 16 logs per lane and the kernel took 17 us, profiles/r2g_*); the four warp sums are added in a fixed order.
+// chain of 16 logs per lane and the kernel took 17 us, profiles/r2_ncu_launch_shares.txt); the four warp sums are added in a fixed order.
 constexpr int kObjWarpsPerRow = 4, kObjRowsPerBlock = 2;
 __global__ void __launch_bounds__(kObjWarpsPerRow * kObjRowsPerBlock * 32)
 objective_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ WH, int ldwh, int T, int F,

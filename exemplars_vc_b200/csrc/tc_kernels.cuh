@@ -48,7 +48,7 @@ using namespace umma;
 
 // Row pitch (elements) of every K-major operand: a multiple of 128 bytes, so that no 64- or 128-byte row segment a
 // TMA box fetches straddles a 128-byte L2 line (a 1056-byte pitch cost contraction 2 25 % extra L2->SM traffic:
-// profiles/r2b_*).
+// profiles/r2_pitch_before_fix_ncu.txt).
 inline int k_pitch(int F) { return round_up(F, 32); }
 inline int k_pitch16(int F) { return round_up(F, 64); }
 
@@ -266,7 +266,7 @@ __device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, ui
 // frame tile of the ratio in contraction 2 (kShareM = false: pair q takes dictionary-row group P*g + q), the
 // dictionary tile in contraction 1 (kShareM = true: pair q takes frame tile P*s + q) -- and every CTA fetches only a
 // 1/kP slice of that tile, multicasting it to the CTAs of the other pairs that hold the same half: L2 -> SM traffic
-// of the shared operand drops by kP (both contractions are bound by that traffic, profiles/r2c_*).  The ring slots
+// of the shared operand drops by kP (both contractions are bound by that traffic, profiles/r2_ncu_summary.txt).  The ring slots
 // then move in lock step across the cluster: a slot is free when EVERY pair's MMAs have read it (kP commits).
 template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, int kEpi, int kP = 1, bool kShareM = false>
 __global__ void __launch_bounds__(
@@ -648,7 +648,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           float* o = p.out + ((size_t)split * p.T + tb) * p.ld_out + m;
           if (fast && p.out_keep_l2) {
             // split-K partials: 37 MB that the reduction kernel reads right after this one -- keep them in L2 (they
-            // were evicted by the streamed operands and came back from DRAM: 16 % L2 hits, profiles/r2c_*)
+            // were evicted by the streamed operands and came back from DRAM: 16 % L2 hits, profiles/r2_reduce_before_bulk_ncu.txt)
 #pragma unroll
             for (int j = 0; j < 32; ++j) st_global_hint(o + (size_t)j * p.ld_out, __uint_as_float(v[j]), kEvictLast);
           } else if (fast) {
@@ -704,10 +704,10 @@ __device__ __forceinline__ void store_r(const ROut& o, int t, int f, float r) {
 //
 // One block per (frame, 512-column chunk).  The split-K partials of the chunk -- S segments of 2 KB, megabytes apart
 // in the workspace -- are staged in shared memory by cp.async.bulk copies issued by one thread and summed from there:
-// with per-lane 16-byte loads this kernel ran at 2.0 TB/s (the SM's outstanding-miss capacity, profiles/r2c_*),
+// with per-lane 16-byte loads this kernel ran at 2.0 TB/s (the SM's outstanding-miss capacity, profiles/r2_reduce_before_bulk_ncu.txt),
 // bulk copies are not subject to that limit.
 // 256 columns x 64 threads per block: 18 KB of staging at the headline shape, so eleven blocks share an SM and the
-// 3 000 blocks of a launch run in under two waves (512 columns: five per SM, 2.7 waves, 17.6 us -- profiles/r2g_*).
+// 3 000 blocks of a launch run in under two waves (512 columns: five per SM, 2.7 waves, 17.6 us -- profiles/r2_ncu_summary.txt).
 constexpr int kRedCols = 256, kRedThreads = 64, kRedMaxBatch = 32;
 __global__ void __launch_bounds__(kRedThreads)
 reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
