@@ -55,6 +55,76 @@ inline int k_pitch16(int F) { return round_up(F, 64); }
 enum TcEpilogue { TEPI_PARTIAL = 0, TEPI_MU_KL = 1, TEPI_MU_FRO = 2 };
 enum TcPrec { PREC_SPLIT = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
 
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// x -> (x1, x2) = (bf16_rn(x), bf16_rn(x - x1)), two values at a time
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = pack_bf16(a - hf.x, b - hf.y);
+}
+// The K operand of contraction 2 in the mode's format: fp32 R (pitch ldr, pad columns zeroed), bf16 R16, or the
+// two bf16 planes R12 (plane 1 at + plane elements) of the fp32-accurate split.
+struct ROut {
+  float* R; int ldr;
+  __nv_bfloat16* R16; int ldr16;
+  __nv_bfloat16* R12; int ldr12; size_t plane;
+  __host__ __device__ int cols() const { return R12 ? ldr12 : (R16 ? ldr16 : (R ? ldr : 0)); }
+};
+__device__ __forceinline__ void store_r(const ROut& o, int t, int f, float r) {
+  if (o.R && f < o.ldr) o.R[(size_t)t * o.ldr + f] = r;
+  if (o.R16 && f < o.ldr16) o.R16[(size_t)t * o.ldr16 + f] = __float2bfloat16_rn(r);
+  if (o.R12 && f < o.ldr12) {
+    const __nv_bfloat16 r1 = __float2bfloat16_rn(r);
+    o.R12[(size_t)t * o.ldr12 + f] = r1;
+    o.R12[o.plane + (size_t)t * o.ldr12 + f] = __float2bfloat16_rn(r - __bfloat162float(r1));
+  }
+}
+// four consecutive columns f..f+3 (f a multiple of 4, every pitch a multiple of 4): 8- / 16-byte stores
+__device__ __forceinline__ void store_r4(const ROut& o, int t, int f, float4 r) {
+  if (o.R && f < o.ldr) *reinterpret_cast<float4*>(o.R + (size_t)t * o.ldr + f) = r;
+  if (o.R16 && f < o.ldr16) {
+    uint2 v;
+    v.x = pack_bf16(r.x, r.y); v.y = pack_bf16(r.z, r.w);
+    *reinterpret_cast<uint2*>(o.R16 + (size_t)t * o.ldr16 + f) = v;
+  }
+  if (o.R12 && f < o.ldr12) {
+    uint2 hi, lo;
+    split2(r.x, r.y, hi.x, lo.x);
+    split2(r.z, r.w, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(o.R12 + (size_t)t * o.ldr12 + f) = hi;
+    *reinterpret_cast<uint2*>(o.R12 + o.plane + (size_t)t * o.ldr12 + f) = lo;
+  }
+}
+
+constexpr int kRedCols = 256, kRedThreads = 64, kRedMaxBatch = 32, kRedMaxTiles = 1024;
+
+// The split-K sum of contraction 1 (and the ratio R = X / max(A H, eps) formed from it) done by the contraction's OWN
+// CTAs -- the first GEMM's epilogue, no second launch (sklearn _nmf.py:554-571).  Every CTA stores its partial tile,
+// arrives on the frame tile's counter and, once all `contributors` CTAs of that frame tile have arrived, sums a
+// 1/contributors share of the tile's (frame, 256-column) units over the splits in fixed order (bit-identical to
+// reduce_partials_kernel), staging the partials through the now idle operand ring with bulk copies.  All work items
+// are resident at once whenever K is split (plan_c1), so the wait cannot deadlock.  counter[2*tile] counts arrivals,
+// counter[2*tile+1] the CTAs that have passed the wait; the last of those resets both, so nothing is reset by the host.
+struct FusedReduce {
+  int enabled;
+  unsigned int* counter;
+  int contributors;   // CTAs that store partials of one frame tile
+  int nslots;         // staging slots (2: the next batch's copies overlap the current sum)
+  int nb;             // frames per batch (1, 2 or 4)
+  int slot_floats;    // floats per slot: [chunk][S_max][nb][kRedCols] partials | [n_left][nb][left_rows] leftover-row partials
+  int S, S_last, f_last, F;
+  float* WH; int ldwh;
+  const float* L; int left_rows, left_ld;   // leftover-row partials of the fused update (left_rows = 0: none)
+  int n_left;
+  const float* X; int ldx;                  // X != nullptr: emit the ratio too
+  int cols;                                 // columns to write per frame: max(ldwh, ratio pitch)
+  ROut ro;
+};
+
 struct GemmParams {
   int M_total;  // dictionary-side rows: F for contraction 1 / conversion, N for contraction 2
   int T;        // frames
@@ -84,6 +154,8 @@ struct GemmParams {
   int left_ld, left_rows;  // frames pitch, rows pitch
   int out_keep_l2;      // PARTIAL: store with the L2 evict-last hint (split-K partials: the reduction reads them next)
   int debug_flags;      // -DEVC_INSTRUMENT builds only (tools/flag_sweep.sh); always 0 and never read otherwise
+  FusedReduce red;      // PARTIAL: split-K sum (+ ratio) inside this launch
+  int direct_store;     // MU_*: the updated activations leave by per-lane global stores instead of the staged TMA store
 };
 
 // Timing experiments (results are garbage when a flag is set).  The default build compiles every test to `false`.
@@ -91,8 +163,17 @@ struct GemmParams {
 //  16 no H chunk loads / stores       32 no leftover-row partials        64 no TMEM loads
 #ifdef EVC_INSTRUMENT
 #define EVC_DBG(p, bit) (((p).debug_flags & (bit)) != 0)
+// per-role wait / work cycle counters, printed by the first two CTAs when flag 128 is set
+#define EVC_CLK_DECL(...) long long __VA_ARGS__
+#define EVC_CLK(v) v = clock64()
+#define EVC_CLK_ADD(acc, since) acc += clock64() - (since)
+#define EVC_CLK_PRINT(p, ...) do { if (((p).debug_flags & 128) && blockIdx.x < 2) printf(__VA_ARGS__); } while (0)
 #else
 #define EVC_DBG(p, bit) false
+#define EVC_CLK_DECL(...)
+#define EVC_CLK(v)
+#define EVC_CLK_ADD(acc, since)
+#define EVC_CLK_PRINT(p, ...)
 #endif
 
 // vals[j] (j = 0..31) per lane -> returns, in lane L, the sum over all 32 lanes of vals[L]  (31 shuffles).
@@ -221,17 +302,6 @@ __device__ __forceinline__ float quotient(float a, float d, float r) {
   return (q == q) ? q : q0;  // a*r overflowed or a is inf: keep the uncorrected value instead of inf - inf
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
-// x -> (x1, x2) = (bf16_rn(x), bf16_rn(x - x1)), two values at a time
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const float2 hf = __bfloat1622float2(h);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = pack_bf16(a - hf.x, b - hf.y);
-}
 // One frame tile of a ring stage: raw = [kRows x 32 fp32] as TMA wrote it with the 128B swizzle (16-byte chunk c
 // of row r sits at chunk c ^ (r & 7)); p1 / p2 = [kRows x 32 bf16] in the 64B-swizzle layout the MMA descriptors
 // expect (chunk c of row r at chunk c ^ ((r >> 1) & 3)).  A unit is a quarter row: 8 floats in, 16 + 16 bytes out;
@@ -260,6 +330,194 @@ __device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, ui
     *reinterpret_cast<uint4*>(p1 + off) = hi;
     *reinterpret_cast<uint4*>(p2 + off) = lo;
   }
+}
+
+// ---- split-K sum + ratio inside contraction 1 (FusedReduce) ------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_add_release_gpu(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// generic-proxy accesses to global memory <-> the async proxy (bulk copies) that reads the same bytes next
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Called by the 256 threads of the 8 epilogue warps (tid = 0..255) of every CTA after its partial tile is stored.
+// `slot` = this CTA's index among the `contributors` of frame tile `t_tile`; `stage` = the idle operand ring;
+// `bars` = 2 mbarriers (count 1), `sh` = 4 x 16 floats of scratch; tmP = the partials as a 3-D tensor
+// (column, frame, split) with boxes of 256 columns x nb frames x S_max splits.
+//
+// The frame tile is cut into batches of `nb` frames; batch b belongs to contributor b % contributors.  One thread
+// brings a whole batch -- every split's rows of those frames -- with ONE box load per 256 columns (per-(split, frame)
+// 1 KB bulk copies were bound by the copy issue rate: 390 per CTA), double buffered when two batches fit the ring.
+template <int kBlockT>
+__device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CUtensorMap* tmP, int t_tile, int slot,
+                                                   float* stage, uint64_t* bars, float* sh, int tid) {
+  const FusedReduce& r = p.red;
+  EVC_CLK_DECL(c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_a = 0, c_w = 0);
+  EVC_CLK(c_0);
+  // this CTA's batches of the tile: (2) below, after the tile barrier (1)
+  const int g = tid >> 6, t64 = tid & 63;
+  const int t_base = t_tile * kBlockT;
+  const int frames = min(kBlockT, p.T - t_base);
+  const int nb = r.nb, S_max = max(r.S, r.S_last);
+  const int n_batches = frames > 0 ? (frames + nb - 1) / nb : 0;
+  const int ldp = p.ld_out, F_main = p.M_total;
+  const int n_chunks = (ldp + kRedCols - 1) / kRedCols;           // 256-column boxes per partial row
+  const int chunk_floats = S_max * nb * kRedCols;                   // one box in shared memory: [split][frame][256]
+  const int left_floats = r.left_rows > 0 ? r.n_left * nb * r.left_rows : 0;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  float* s_left = sh + 16 * g;       // [8] leftover sums of frame g of the batch | [2] per-warp partials
+  float* s_warp = s_left + 8;
+  auto issue = [&](int b, int s) {   // thread 0: box loads of batch b into slot s
+    const int t = t_base + b * nb;
+    float* dst = stage + (size_t)s * r.slot_floats;
+    const uint32_t bar = bar0 + 8u * s;
+    mbar_arrive_expect_tx(bar, (uint32_t)((n_chunks * chunk_floats + left_floats) * 4));
+    for (int c = 0; c < n_chunks; ++c)
+      tma_load_3d(smem_u32(dst + (size_t)c * chunk_floats), tmP, c * kRedCols, t, 0, bar, kEvictFirst);
+    if (left_floats > 0)  // [l][frame][row]: the frames of a batch are contiguous in the leftover partials
+      for (int l = 0; l < r.n_left; ++l)
+        bulk_load_1d(smem_u32(dst + (size_t)n_chunks * chunk_floats + (size_t)l * nb * r.left_rows),
+                     r.L + ((size_t)l * r.left_ld + t) * r.left_rows, (uint32_t)(nb * r.left_rows) * 4u, bar, kEvictFirst);
+  };
+  // X entries of this thread's first float4 of a batch and of its first tail column (prefetched one batch ahead)
+  auto load_x4 = [&](int t, int f) {
+    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!r.X || t >= p.T) return x4;
+    if (f + 3 < r.F && ((r.ldx & 3) == 0) && ((((uintptr_t)r.X) & 15) == 0))
+      return __ldg(reinterpret_cast<const float4*>(r.X + (size_t)t * r.ldx + f));
+    float* xs = reinterpret_cast<float*>(&x4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (f + j < r.F) xs[j] = r.X[(size_t)t * r.ldx + f + j];
+    return x4;
+  };
+  float4 x_main = make_float4(0.f, 0.f, 0.f, 0.f);
+  float x_tail = 0.f;
+  auto prefetch_x = [&](int bb) {
+    if (!r.X || bb >= n_batches) return;
+    const int c4 = ldp >> 2, tb = t_base + bb * nb;
+    if (tid < nb * c4) {
+      const int fr = tid / c4, f = (tid - fr * c4) * 4;
+      if (f < F_main) x_main = load_x4(tb + fr, f);
+    }
+    if (g < nb && tb + g < p.T && F_main + t64 < r.F && r.left_rows > 0) x_tail = r.X[(size_t)(tb + g) * r.ldx + F_main + t64];
+  };
+  int b = slot, k = 0;
+  uint32_t phases = 0;
+  prefetch_x(b);  // (the inputs do not depend on the other CTAs: in flight across the tile barrier)
+
+  // (1) publish this CTA's partials, wait for the other contributors of the frame tile
+  __threadfence();
+  fence_proxy_async_global();
+  named_bar_sync(1, kEpiWarps * 32);
+  EVC_CLK(c_1);
+  if (tid == 0) {
+    unsigned int* ctr = r.counter + 2 * t_tile;
+    atom_add_release_gpu(ctr, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(ctr) < (unsigned int)r.contributors) {
+      if (clock64() - t0 > 4000000000ll) {
+        printf("evc: split-K tile barrier timed out (block %d, frame tile %d: %u of %d arrived)\n", (int)blockIdx.x,
+               t_tile, ld_acquire_gpu(ctr), r.contributors);
+        __trap();
+      }
+    }
+    // everybody is past the point of incrementing; the last CTA through resets both counters for the next launch
+    if (atom_add_release_gpu(ctr + 1, 1u) == (unsigned int)r.contributors - 1u) {
+      ctr[0] = 0u;
+      ctr[1] = 0u;
+    }
+    __threadfence();
+    fence_proxy_async_global();
+  }
+  named_bar_sync(1, kEpiWarps * 32);
+  EVC_CLK(c_2);
+
+  if (tid == 0) {
+    if (b < n_batches) issue(b, 0);
+    if (r.nslots == 2 && b + r.contributors < n_batches) issue(b + r.contributors, 1);
+  }
+  for (; b < n_batches; b += r.contributors, ++k) {
+    const int s = (r.nslots == 2) ? (k & 1) : 0;
+    const float* st = stage + (size_t)s * r.slot_floats;
+    const int t_b = t_base + b * nb;
+    EVC_CLK(c_a);
+    mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
+    EVC_CLK_ADD(c_w, c_a);
+    phases ^= 1u << s;
+    // leftover rows (the Nyquist bin): 64-thread group g sums frame g of the batch, in reduce_partials_kernel's order
+    if (left_floats > 0 && g < nb) {
+      const float* lst = st + (size_t)n_chunks * chunk_floats;
+      for (int l = 0; l < r.n_left; ++l) {
+        const float* row = lst + ((size_t)l * nb + g) * r.left_rows;
+        float a = 0.f;
+        for (int q = t64; q < r.left_rows; q += kRedThreads) a += row[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((t64 & 31) == 0) s_warp[t64 >> 5] = a;
+        named_bar_sync(2 + g, kRedThreads);
+        if (t64 == 0) s_left[l] = s_warp[0] + s_warp[1];
+        named_bar_sync(2 + g, kRedThreads);
+      }
+    }
+    // tensor-core columns: float4 per thread, splits summed in order (deterministic)
+    const int c4_per_frame = ldp >> 2;
+    for (int idx = tid, it = 0; idx < nb * c4_per_frame; idx += kEpiWarps * 32, ++it) {
+      const int fr = idx / c4_per_frame, f = (idx - fr * c4_per_frame) * 4, t = t_b + fr;
+      if (t >= p.T || f >= F_main) continue;
+      const int c = f / kRedCols;
+      const int n = (f >= r.f_last) ? r.S_last : r.S;
+      const float4 x4 = (it == 0) ? x_main : load_x4(t, f);
+      const float* src = st + (size_t)c * chunk_floats + (size_t)fr * kRedCols + (f - c * kRedCols);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kk = 0; kk < n; ++kk) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)kk * nb * kRedCols);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      if (f + 3 < F_main) {  // whole group inside the tensor-core rows: vector stores
+        if (f < r.ldwh) *reinterpret_cast<float4*>(r.WH + (size_t)t * r.ldwh + f) = acc;
+        if (r.X)
+          store_r4(r.ro, t, f, make_float4(__fdiv_rn(x4.x, fmaxf(acc.x, p.eps)), __fdiv_rn(x4.y, fmaxf(acc.y, p.eps)),
+                                           __fdiv_rn(x4.z, fmaxf(acc.z, p.eps)), __fdiv_rn(x4.w, fmaxf(acc.w, p.eps))));
+      } else {
+        const float sv[4] = {acc.x, acc.y, acc.z, acc.w};
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (f + j >= F_main) break;
+          if (f + j < r.ldwh) r.WH[(size_t)t * r.ldwh + f + j] = sv[j];
+          if (r.X) store_r(r.ro, t, f + j, (f + j < r.F) ? __fdiv_rn(xv[j], fmaxf(sv[j], p.eps)) : 0.f);
+        }
+      }
+    }
+    // columns past the tensor-core rows: the leftover rows, then zero padding
+    if (g < nb && t_b + g < p.T) {
+      const int t = t_b + g;
+      for (int f = F_main + t64, it = 0; f < r.cols; f += kRedThreads, ++it) {
+        const bool have = f < r.F && r.left_rows > 0;
+        const float sum = have ? s_left[f - F_main] : 0.f;
+        if (f < r.ldwh && (have || f >= r.F)) r.WH[(size_t)t * r.ldwh + f] = sum;
+        if (r.X) store_r(r.ro, t, f, have ? __fdiv_rn(it == 0 ? x_tail : r.X[(size_t)t * r.ldx + f], fmaxf(sum, p.eps)) : 0.f);
+      }
+    }
+    // this thread's X entries of the CTA's next batch, fetched under the barrier and the next wait
+    prefetch_x(b + r.contributors);
+    named_bar_sync(1, kEpiWarps * 32);  // the slot (and s_left) may be overwritten
+    const int bn = b + r.nslots * r.contributors;
+    if (tid == 0 && bn < n_batches) issue(bn, s);
+  }
+  EVC_CLK(c_3);
+  if (tid == 0)
+    EVC_CLK_PRINT(p, "clk cta %d fused reduce: fence %lld barrier %lld reduce %lld (waiting for copies %lld, %d batches)\n", (int)blockIdx.x,
+                  c_1 - c_0, c_2 - c_1, c_3 - c_2, c_w, k);
 }
 
 // kP = CTA pairs per cluster.  With kP > 1 the pairs of a cluster work on items that share one operand tile -- the
@@ -294,6 +552,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_hready[kHBufs];  // the 4 epilogue warps of a chunk wrote the updated values
   __shared__ __align__(8) uint64_t bar_hempty[kHBufs];  // the TMA store has read the buffer
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(8) uint64_t bar_red[2];          // FusedReduce: the partials of a batch landed (one per slot)
+  __shared__ float red_sh[64];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -309,7 +569,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     tma_prefetch_desc(&tmN);
     if (kStageH) tma_prefetch_desc(&tmH);
     if (Cfg::kShadow) tma_prefetch_desc(&tmS);
-    if (kFro) tma_prefetch_desc(&tmQ);
+    if (kFro || (kEpi == TEPI_PARTIAL && p.red.enabled)) tma_prefetch_desc(&tmQ);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), Cfg::kFullArrivals);
       mbar_init(smem_u32(&bar_raw[i]), 1);
@@ -322,8 +582,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     for (int i = 0; i < kHBufs; ++i) {
       mbar_init(smem_u32(&bar_hfull[i]), 1);
       mbar_init(smem_u32(&bar_hready[i]), 4);
-      mbar_init(smem_u32(&bar_hempty[i]), 1);
+      mbar_init(smem_u32(&bar_hempty[i]), (p.direct_store && !Cfg::kShadow) ? 4 : 1);  // the storer's TMA store read it | the 4 warps consumed it
     }
+    if (kEpi == TEPI_PARTIAL)
+      for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&bar_red[i]), 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc2(smem_u32(&tmem_base_smem), 512); tmem_relinquish2(); }
@@ -366,13 +628,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wait = 0);
+      EVC_CLK(c_t0);
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = item_of(item);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles) + (int)rank * 128;
         // (a half-width item still loads a kNRows-row box: the narrower MMA never reads the surplus rows)
         const int t0 = w.t_tile * kBlockT + w.t_off + (int)rank * (w.t_cols / kCG);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          EVC_CLK(c_a);
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          EVC_CLK_ADD(c_wait, c_a);
           const uint32_t full = full_leader + (uint32_t)stage * 8u;
           if (EVC_DBG(p, 4)) {
             if (rank == 0) mbar_arrive(smem_u32(&bar_full[stage]));
@@ -414,21 +680,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      EVC_CLK_PRINT(p, "clk cta %d producer: total %lld wait_empty %lld\n", (int)blockIdx.x, clock64() - c_t0, c_wait);
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA of the pair only) =================
     if (lane == 0 && rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wacc = 0, c_wfull = 0);
+      EVC_CLK(c_t0);
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = item_of(item);
         const int m0 = w.m_group * (Cfg::kRowsPerSub * kMTiles);
         const int kb0 = w.kb0, kb1 = w.kb1;
         const uint32_t idesc = (w.t_cols == kBlockT) ? kIdesc : make_idesc(kFmt, 128 * kCG, (uint32_t)w.t_cols);
+        EVC_CLK(c_a);
         mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1u);
+        EVC_CLK_ADD(c_wacc, c_a);
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
+          EVC_CLK(c_a);
           mbar_wait(smem_u32(&bar_full[stage]), phase);
+          EVC_CLK_ADD(c_wfull, c_a);
           tc_fence_after();
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
           const uint32_t nbase = sbase + Cfg::kOffN;
@@ -467,11 +740,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         mma_commit_mc(smem_u32(&bar_acc_full[acc]), pair_mask);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
       }
+      EVC_CLK_PRINT(p, "clk cta %d mma: total %lld wait_acc_empty %lld wait_full %lld\n", (int)blockIdx.x, clock64() - c_t0, c_wacc, c_wfull);
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp) {
     // ================= H chunk loader: prefetches the activations the epilogue will update =================
     if (lane == 0) {
       int hbase = 0;
+      EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wait = 0);
+      EVC_CLK(c_t0);
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = item_of(item);
         const int t0 = w.t_tile * kBlockT + w.t_off;
@@ -483,7 +759,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const int n0 = (w.m_group * kMTiles + i) * Cfg::kRowsPerSub + (int)rank * 128;
           const int seq = hbase + cc, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
+          EVC_CLK(c_a);
           mbar_wait(smem_u32(&bar_hempty[b]), ph ^ 1u);
+          EVC_CLK_ADD(c_wait, c_a);
           const uint32_t full = smem_u32(&bar_hfull[b]);
           if (EVC_DBG(p, 16)) { mbar_arrive(full); continue; }
           mbar_arrive_expect_tx(full, (uint32_t)Cfg::kHBufStride);
@@ -493,11 +771,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         }
         hbase += nsub * nch;
       }
+      EVC_CLK_PRINT(p, "clk cta %d hloader: total %lld wait_hempty %lld\n", (int)blockIdx.x, clock64() - c_t0, c_wait);
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp + 1) {
     // ================= H chunk storer =================
-    if (lane == 0) {
+    if (lane == 0 && !(p.direct_store && !Cfg::kShadow)) {
       int hbase = 0;
+      EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wait = 0, c_wread = 0);
+      EVC_CLK(c_t0);
       for (int item = first_item; item < num_items; item += item_stride) {
         const WorkItem w = item_of(item);
         const int t0 = w.t_tile * kBlockT + w.t_off;
@@ -508,18 +789,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const int n0 = (w.m_group * kMTiles + i) * Cfg::kRowsPerSub + (int)rank * 128;
           const int seq = hbase + cc, b = seq % kHB;
           const uint32_t ph = (uint32_t)(seq / kHB) & 1u;
+          EVC_CLK(c_a);
           mbar_wait(smem_u32(&bar_hready[b]), ph);
+          EVC_CLK_ADD(c_wait, c_a);
           if (!EVC_DBG(p, 16)) {
             tma_store_2d(&tmH, n0, t0 + c * kHChunkT, ring + Cfg::kOffH + b * Cfg::kHBufStride);
             if (Cfg::kShadow) tma_store_2d(&tmS, n0, t0 + c * kHChunkT, ring + Cfg::kOffS + b * Cfg::kSBufBytes);
             tma_store_commit();
+            EVC_CLK(c_a);
             tma_store_wait_read();
+            EVC_CLK_ADD(c_wread, c_a);
           }
           mbar_arrive(smem_u32(&bar_hempty[b]));
         }
         hbase += nsub * nch;
       }
       tma_store_wait_all();
+      EVC_CLK_PRINT(p, "clk cta %d hstorer: total %lld wait_hready %lld wait_store_read %lld\n", (int)blockIdx.x, clock64() - c_t0, c_wait, c_wread);
     }
   } else {
     // ================= epilogue: 8 warps.  Warp w may touch TMEM lanes [32*(w%4), +32); the two warps
@@ -529,6 +815,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     const int half = (warp - 2) >> 2;
     int acc = 0, stage = 0, hbase = 0;
     uint32_t acc_phase = 0, phase = 0;
+    EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wacc = 0, c_wh = 0, c_wraw = 0, c_red = 0);
+    EVC_CLK(c_t0);
     for (int item = first_item; item < num_items; item += item_stride) {
       const WorkItem w = item_of(item);
       const int m_group = w.m_group, split = w.split;
@@ -539,7 +827,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         // stage, so every warp observes every phase of bar_raw
         const int tid = threadIdx.x - 64;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          EVC_CLK(c_a);
           mbar_wait(smem_u32(&bar_raw[stage]), phase);
+          EVC_CLK_ADD(c_wraw, c_a);
           uint8_t* sb = ring_ptr + stage * Cfg::kStageBytes;
           if (!EVC_DBG(p, 1))
             split_planes<Cfg::kNRows>(sb + Cfg::kOffRaw, sb + Cfg::kOffN, sb + Cfg::kOffN + Cfg::kNPlaneBytes, tid);
@@ -549,7 +839,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+      EVC_CLK(c_a);
       mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase);
+      EVC_CLK_ADD(c_wacc, c_a);
       tc_fence_after();
       if (kStageH) {
         // ---- fused multiplicative update through the shared-memory H chunks ----
@@ -574,7 +866,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           uint32_t v[32];
           if (!EVC_DBG(p, 64))
             tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * kMTiles + i) * kBlockT + c * 32), v);
+          EVC_CLK(c_a);
           mbar_wait(smem_u32(&bar_hfull[b]), ph);
+          EVC_CLK_ADD(c_wh, c_a);
           float* hb = reinterpret_cast<float*>(ring_ptr + Cfg::kOffH + b * Cfg::kHBufStride) + quarter * 32 + lane;
           float h[32];
 #pragma unroll
@@ -608,11 +902,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) sbuf[j * 128] = __float2bfloat16_rn(h[j]);
           }
+          if (p.direct_store && !Cfg::kShadow) {
+            // straight to global memory: a warp writes 32 consecutive exemplars of one frame (128 bytes) per store;
+            // the chunk buffer is free as soon as its values are in registers
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_hempty[b]));
+            if (m < p.M_total) {
+              float* g = p.out + (size_t)tbm * p.ld_out + m;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) hb[j * 128] = h[j];
-          fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA store
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_hready[b]));
+              for (int j = 0; j < 32; ++j)
+                if (tbm + j < p.T) g[(size_t)j * p.ld_out] = h[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) hb[j * 128] = h[j];
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_hready[b]));
+          }
 #pragma unroll
           for (int l = 0; l < 8; ++l) {
             if (l >= p.n_left || EVC_DBG(p, 32)) break;
@@ -661,11 +968,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           }
         }
       }
+      if (kEpi == TEPI_PARTIAL && p.red.enabled) {
+        // split-K sum (+ ratio) by the contraction's own CTAs; one item per pair in this mode, the ring is idle
+        const int groups = p.splits_last ? p.num_m_groups - 1 : p.num_m_groups;
+        const int idx = (item < p.items_main) ? w.m_group + groups * split : groups * p.num_splits + split;
+        EVC_CLK(c_a);
+        fused_reduce_phase<kBlockT>(p, &tmQ, w.t_tile, idx * kCG + (int)rank, reinterpret_cast<float*>(ring_ptr), bar_red,
+                                    red_sh, (int)threadIdx.x - 64);
+        EVC_CLK_ADD(c_red, c_a);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&bar_acc_empty[acc]), leader));
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1u; }
     }
+    if (lane == 0 && (warp == 2 || warp == 6))
+      EVC_CLK_PRINT(p, "clk cta %d epilogue warp %d: total %lld wait_acc_full %lld wait_hfull %lld wait_raw %lld fused_reduce %lld\n",
+                    (int)blockIdx.x, warp, clock64() - c_t0, c_wacc, c_wh, c_wraw, c_red);
   }
 
   tc_fence_before();
@@ -680,24 +999,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 
 // ---- memory-bound helpers ------------------------------------------------------------------------
 
-// The K operand of contraction 2 in the mode's format: fp32 R (pitch ldr, pad columns zeroed), bf16 R16, or the
-// two bf16 planes R12 (plane 1 at + plane elements) of the fp32-accurate split.
-struct ROut {
-  float* R; int ldr;
-  __nv_bfloat16* R16; int ldr16;
-  __nv_bfloat16* R12; int ldr12; size_t plane;
-  __host__ __device__ int cols() const { return R12 ? ldr12 : (R16 ? ldr16 : (R ? ldr : 0)); }
-};
-__device__ __forceinline__ void store_r(const ROut& o, int t, int f, float r) {
-  if (o.R && f < o.ldr) o.R[(size_t)t * o.ldr + f] = r;
-  if (o.R16 && f < o.ldr16) o.R16[(size_t)t * o.ldr16 + f] = __float2bfloat16_rn(r);
-  if (o.R12 && f < o.ldr12) {
-    const __nv_bfloat16 r1 = __float2bfloat16_rn(r);
-    o.R12[(size_t)t * o.ldr12 + f] = r1;
-    o.R12[o.plane + (size_t)t * o.ldr12 + f] = __float2bfloat16_rn(r - __bfloat162float(r1));
-  }
-}
-
 // WH[t,f] = sum_s P[s][t][f] for the tensor-core rows f < F_main (fixed order: deterministic);
 // WH[t,F_main+l] = sum_r L[l][t][r] from the fused update's per-warp partials when `left_rows` > 0.
 // With `X` != nullptr it also emits the ratio R = X / max(WH, eps) (zero pad columns) in the same pass.
@@ -708,7 +1009,6 @@ __device__ __forceinline__ void store_r(const ROut& o, int t, int f, float r) {
 // bulk copies are not subject to that limit.
 // 256 columns x 64 threads per block: 18 KB of staging at the headline shape, so eleven blocks share an SM and the
 // 3 000 blocks of a launch run in under two waves (512 columns: five per SM, 2.7 waves, 17.6 us -- profiles/r2_ncu_summary.txt).
-constexpr int kRedCols = 256, kRedThreads = 64, kRedMaxBatch = 32;
 __global__ void __launch_bounds__(kRedThreads)
 reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
                        float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
@@ -937,6 +1237,25 @@ inline int make_tmap16(CUtensorMap* m, const __nv_bfloat16* base, long long rows
   return make_tmap_any(m, base, 2, rows, cols, ld, box_cols, box_rows, true);
 }
 
+// fp32 tensor (d2, d1, d0) with d0 contiguous, row pitch ld0 elements and plane pitch ld1 elements; box b0 x b1 x b2,
+// no swizzle (the split-K partials [split][frame][column] read back by contraction 1's own CTAs).
+inline int make_tmap3d(CUtensorMap* m, const float* base, int d0, int d1, int d2, size_t ld0, size_t ld1, int b0, int b1,
+                       int b2) {
+  PFN_encodeTiled enc;
+  EVC_TRY(get_encode(&enc));
+  if (((uintptr_t)base & 15) || ((ld0 * 4) & 15) || ((ld1 * 4) & 15) || b0 > 256 || b1 > 256 || b2 > 256)
+    return fail(EVC_ERR_INVALID_ARGUMENT, "bad 3-D tensor map (pitches %zu %zu, box %d %d %d)", ld0, ld1, b0, b1, b2);
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld0 * 4, (cuuint64_t)ld1 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EVC_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+  return EVC_OK;
+}
+
 // SM count of the CURRENT device (a process may hold dictionaries on several GPUs)
 inline int num_sms() {
   static int cache[64] = {0};
@@ -1086,11 +1405,12 @@ struct DictOperands {
   CUtensorMap tmAT16_s[2], tmBT16_s[2];  // the same with 64- and 32-row boxes: the slices clusters of 2 / 4 pairs multicast
   DevBuf h16, r16;  // per solve: bf16 shadow of H (BF16 mode); the ratio as bf16 / as two bf16 planes
   long long r_rows = 0;  // rows per plane of r16 in the split mode
+  DevBuf red_ctr;        // FusedReduce: arrival / passed counters per frame tile (zero between launches)
   void release() {
     cudaFree(AT); cudaFree(BT); cudaFree(A16); cudaFree(AT16); cudaFree(BT16); cudaFree(ATleft); cudaFree(BTleft);
     AT = BT = ATleft = BTleft = nullptr;
     A16 = AT16 = BT16 = nullptr;
-    h16.release(); r16.release();
+    h16.release(); r16.release(); red_ctr.release();
   }
 };
 
@@ -1112,6 +1432,8 @@ inline int build_operands(DictOperands* o, int mode, const float* A, const float
   o->n_left = (F > 128 && (F % 128) <= 8 && !getenv("EVC_NO_LEFTOVER")) ? F % 128 : 0;
   o->F_main = F - o->n_left;
   const size_t at_bytes = (size_t)F * o->ldN * sizeof(float);
+  EVC_TRY(o->red_ctr.reserve(2 * kRedMaxTiles * sizeof(unsigned int)));
+  EVC_CUDA(cudaMemsetAsync(o->red_ctr.p, 0, o->red_ctr.bytes, s));
   dim3 tb(32, 8), tg(ceil_div(N, 32), ceil_div(F, 32));
   // fp32 transposes: resident operands in TF32 mode, staging for the bf16 copies (and the leftover rows) otherwise
   EVC_CUDA(cudaMalloc(&o->AT, at_bytes));
@@ -1342,22 +1664,56 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   p.m_plane_rows = (int)o.at_rows; p.n_plane_rows = 0;
   p.out = partials; p.ld_out = pl.ldp;
   p.out_keep_l2 = getenv("EVC_NO_KEEP_L2") ? 0 : 1;
+  // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
+  const bool from_partials = o.n_left > 0 && !target && o.left_valid;
+  const bool standalone = o.n_left > 0 && !from_partials;
+  const bool fuse = ra && !standalone;  // the ratio is formed in the same pass as the split-K sum
+  const ROut ro = fuse ? ratio_out(o, mode, ra->R, ra->ldR) : ROut{};
+  const int cols = std::max(ldWH, fuse ? ro.cols() : 0);
+  const int lrows = from_partials ? left_rows(o, mode) : 0;
+  // The sum (+ ratio) runs inside the contraction itself when every work item is resident at once (always the case
+  // when K is split) and a unit's partials fit the staging slots the idle operand ring offers; else a second launch.
+  using L1 = TcLaunch<kC1MTiles, kC1BlockT, kPrec, kSplitN, TEPI_PARTIAL, kP, true>;
+  bool in_kernel = false;
+  CUtensorMap tmP = tmH;  // the partials as a (column, frame, split) tensor when the sum runs in the kernel
+  {
+    static const bool allow = getenv("EVC_NO_FUSED_REDUCE") == nullptr;
+    const int items = p.items_main + p.splits_last * p.num_t_tiles;
+    const size_t ring_floats = (size_t)L1::Cfg::kStages * L1::Cfg::kStageBytes / sizeof(float);
+    const int n_chunks = ceil_div(pl.ldp, kRedCols);
+    // frames per batch / slots: the most frames per box load such that two batches (double buffering) fit the ring
+    int nb = 0, nslots = 0;
+    size_t slot_floats = 0;
+    for (int cand_slots = 2; cand_slots >= 1 && !nb; --cand_slots)
+      for (int cand = 4; cand >= 1 && !nb; cand >>= 1) {
+        const size_t sf = round_up_sz((size_t)n_chunks * pl.max_splits * cand * kRedCols + (size_t)o.n_left * cand * lrows, 32);
+        if (cand_slots * sf <= ring_floats) { nb = cand; nslots = cand_slots; slot_floats = sf; }
+      }
+    if (allow && nb > 0 && items <= L1::slots() && pl.t_tiles * kP <= kRedMaxTiles && o.red_ctr.p && pl.max_splits <= 256) {
+      in_kernel = true;
+      EVC_TRY(make_tmap3d(&tmP, partials, pl.ldp, T, pl.max_splits, (size_t)pl.ldp, (size_t)T * pl.ldp, kRedCols, nb,
+                          pl.max_splits));
+      FusedReduce& r = p.red;
+      r.enabled = 1; r.counter = o.red_ctr.as<unsigned int>();
+      r.contributors = ((pl.splits_last ? pl.m_groups - 1 : pl.m_groups) * pl.splits + pl.splits_last) * kCG;
+      r.nslots = nslots; r.nb = nb; r.slot_floats = (int)slot_floats;
+      r.S = pl.splits; r.S_last = pl.splits_last; r.f_last = pl.f_last; r.F = o.F;
+      r.WH = WH; r.ldwh = ldWH;
+      r.L = leftp; r.left_rows = lrows; r.left_ld = left_ld(T); r.n_left = o.n_left;
+      r.X = fuse ? ra->X : nullptr; r.ldx = fuse ? ra->ldX : 0;
+      r.cols = cols; r.ro = ro;
+      p.eps = fuse ? ra->eps : 0.f;
+    }
+  }
   {
     ProfScope ps(0, s);
     const CUtensorMap& tmD = (kPrec == PREC_TF32) ? (target ? o.tmBT : o.tmAT)
                              : (kP == 1)          ? (target ? o.tmBT16 : o.tmAT16)
                                                   : (target ? o.tmBT16_s[kP / 4] : o.tmAT16_s[kP / 4]);
-    EVC_TRY((TcLaunch<kC1MTiles, kC1BlockT, kPrec, kSplitN, TEPI_PARTIAL, kP, true>::launch(tmD, tmH, tmH, tmH, tmH, p, s)));
+    EVC_TRY((L1::launch(tmD, tmH, tmH, tmP, tmH, p, s)));
   }
-  // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
-  const bool from_partials = o.n_left > 0 && !target && o.left_valid;
-  const bool standalone = o.n_left > 0 && !from_partials;
-  {
+  if (!in_kernel) {
     ProfScope ps(1, s);
-    const bool fuse = ra && !standalone;
-    const ROut ro = fuse ? ratio_out(o, mode, ra->R, ra->ldR) : ROut{};
-    const int cols = std::max(ldWH, fuse ? ro.cols() : 0);
-    const int lrows = from_partials ? left_rows(o, mode) : 0;
     const int batch = std::max(1, std::min(kRedMaxBatch, pl.max_splits));
     const size_t smem = ((size_t)batch * kRedCols + (size_t)o.n_left * lrows) * sizeof(float);
     static bool configured[64] = {false};
@@ -1378,12 +1734,13 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
                                 pl.ldp, o.F, o.F_main, WH, ldWH, (const float*)leftp, lrows, o.n_left, left_ld(T),
                                 fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0, fuse ? ra->eps : 0.f, ro, batch));
     EVC_LAUNCH_CHECK();
-    if (standalone) {
-      const float* rows = (mode == EVC_MODE_TF32) ? (target ? o.BT : o.AT) + (size_t)o.F_main * o.ldN
-                                                  : (target ? o.BTleft : o.ATleft);
-      leftover_rows_kernel<<<T, 256, 0, s>>>(H, ldH, T, o.N, rows, o.ldN, o.n_left, WH, ldWH, o.F_main);
-      EVC_LAUNCH_CHECK();
-    }
+  }
+  if (standalone) {
+    ProfScope ps(1, s);
+    const float* rows = (mode == EVC_MODE_TF32) ? (target ? o.BT : o.AT) + (size_t)o.F_main * o.ldN
+                                                : (target ? o.BTleft : o.ATleft);
+    leftover_rows_kernel<<<T, 256, 0, s>>>(H, ldH, T, o.N, rows, o.ldN, o.n_left, WH, ldWH, o.F_main);
+    EVC_LAUNCH_CHECK();
   }
   if (ra && standalone) EVC_TRY(launch_ratio(o, mode, ra->X, ra->ldX, WH, ldWH, ra->R, ra->ldR, T, o.F, ra->eps, 0, s));
   return EVC_OK;
@@ -1435,6 +1792,10 @@ inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR
   }
   // neighbouring CTA pairs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
   p.m_fastest = 1;
+  {
+    static const bool direct = getenv("EVC_C2_DIRECT_STORE") != nullptr && atoi(getenv("EVC_C2_DIRECT_STORE")) != 0;
+    p.direct_store = direct ? 1 : 0;
+  }
   CUtensorMap tmHc = tmR, tmQc = tmR, tmSc = tmR;  // the fused updates stage H (and the Frobenius numerator) through shared memory
   if (kPrec == PREC_BF16 && kEpi != TEPI_PARTIAL)  // ... and the bf16 shadow of H leaves the same way
     EVC_TRY(make_tmap_any(&tmSc, o.h16.as<__nv_bfloat16>(), 2, T, o.N, o.ldN16, 128, kHChunkT, false));

@@ -120,6 +120,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// 3-D box load (no swizzle): coordinates c0 (contiguous) / c1 / c2.
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t bar,
+                                            uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
 
 // Same load issued by a CTA of a pair (cta_group::2): the data lands in THIS CTA's shared memory, the transaction
 // bytes are credited to `bar_cluster`, a shared::cluster address that may name the LEADER CTA's barrier (mapa_rank),

@@ -215,3 +215,22 @@ def test_content_keyed_cache_is_used_and_never_stale(tmp_path):
             assert len(os.listdir(tmp_path)) == 2 and not np.all(H2["H_stft"] == 7.0)
     finally:
         m.cache_dir, m.use_stft = old
+
+
+def test_in_kernel_split_k_sum_equals_the_separate_reduction_pass():
+    """The split-K sum + ratio done by contraction 1's own CTAs (the first GEMM's epilogue, sklearn _nmf.py:554-571)
+    gives bit for bit the results of the separate reduce_partials_kernel launch it replaces (EVC_NO_FUSED_REDUCE=1),
+    at six shapes (split-K with and without leftover rows, several row groups, no split at T = 19000) in all three
+    tensor-core modes.  The switch is read once per process, so each variant runs in its own interpreter."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "manual", "fused_reduce_ab.py")
+    outs = []
+    for extra in ({}, {"EVC_NO_FUSED_REDUCE": "1"}):
+        env = dict(os.environ, **extra)
+        env.pop("EVC_NO_FUSED_REDUCE", None) if not extra else None
+        r = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if " H " in l])
+    assert len(outs[0]) == 18 and outs[0] == outs[1], "\n".join(f"{a}\n{b}" for a, b in zip(*outs) if a != b)

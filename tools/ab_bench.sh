@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 for spec in "$@"; do
   tag="${spec%%:*}"; envs="${spec#*:}"
-  env $envs timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err || echo "variant $tag failed"
+  env $envs timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err || echo "variant $tag failed"
   python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]
