@@ -110,7 +110,7 @@ constexpr int kRedCols = 256, kRedThreads = 64, kRedMaxBatch = 32, kRedMaxTiles 
 // are resident at once whenever K is split (plan_c1), so the wait cannot deadlock.  counter[2*tile] counts arrivals,
 // counter[2*tile+1] the CTAs that have passed the wait; the last of those resets both, so nothing is reset by the host.
 struct FusedReduce {
-  int enabled;
+  int enabled;        // 1: tile barrier + sum over the splits; 2: K not split, the epilogue writes A*H / the ratio from TMEM
   unsigned int* counter;
   int contributors;   // CTAs that store partials of one frame tile
   int nslots;         // staging slots (2: the next batch's copies overlap the current sum)
@@ -119,6 +119,7 @@ struct FusedReduce {
   int S, S_last, f_last, F;
   float* WH; int ldwh;
   const float* L; int left_rows, left_ld;   // leftover-row partials of the fused update (left_rows = 0: none)
+  const float* Lp; int lp_splits;            // ... or contraction 1's own per-split sums [split][row][frame] (fp32-accurate mode)
   int n_left;
   const float* X; int ldx;                  // X != nullptr: emit the ratio too
   int cols;                                 // columns to write per frame: max(ldwh, ratio pitch)
@@ -260,8 +261,10 @@ struct TileCfg {
   static constexpr int kNPlaneBytes = kNRows * kRowBytes;
   static constexpr int kNBytes = kPlanes * kNPlaneBytes;
   static constexpr int kRawBytes = kSplitN ? kNRows * 128 : 0;           // fp32 frame tile the planes are derived from
-  static constexpr int kOffN = kMBytes, kOffRaw = kMBytes + kNBytes;
-  static constexpr int kStageBytes = kMBytes + kNBytes + kRawBytes;
+  // kSplitN: this K-block of the dictionary rows that stay off the tensor cores (F_main.., at most 8): [8][32] fp32
+  static constexpr int kLeftBytes = kSplitN ? 8 * 128 : 0;
+  static constexpr int kOffN = kMBytes, kOffRaw = kMBytes + kNBytes, kOffLeft = kMBytes + kNBytes + kRawBytes;
+  static constexpr int kStageBytes = kMBytes + kNBytes + kRawBytes + kLeftBytes;
   // bytes per CTA per stage that TMA credits to the leader's "full" barrier
   static constexpr int kTxBytes = kMBytes + (kSplitN ? 0 : kNBytes);
   // arrivals on the leader's "full" barrier: its producer's expect_tx + (kSplitN) every split warp of both CTAs
@@ -307,8 +310,14 @@ __device__ __forceinline__ float quotient(float a, float d, float r) {
 // expect (chunk c of row r at chunk c ^ ((r >> 1) & 3)).  A unit is a quarter row: 8 floats in, 16 + 16 bytes out;
 // the 256 threads of the 8 epilogue warps take kRows*4/256 units each.  Bank-conflict free: a quarter-warp reads /
 // writes eight distinct 16-byte columns of two adjacent rows.
+//
+// With n_left > 0 the same registers also feed the dictionary rows that stay off the tensor cores (the Nyquist bin
+// of a 513-bin spectrum): lacc[q][l] += sum_e x[8c + e] * aleft[l][8c + e] for this thread's quarter rows -- the
+// activations pass through these registers anyway, and these warps have time to spare (they wait for TMA two thirds
+// of the main loop).  aleft = [8][32] fp32, this K-block of rows F_main.. of the transposed dictionary.
 template <int kRows>
-__device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, uint8_t* p2, int tid) {
+__device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, uint8_t* p2, int tid, const float* aleft,
+                                             int n_left, float (&lacc)[kRows * 4 / (kEpiWarps * 32)][8]) {
   constexpr int kPer = kRows * 4 / (kEpiWarps * 32);
   float4 x[kPer][2];
 #pragma unroll
@@ -317,6 +326,22 @@ __device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, ui
     const uint8_t* r = raw + row * 128;
     x[q][0] = *reinterpret_cast<const float4*>(r + (((2 * c) ^ sw) << 4));
     x[q][1] = *reinterpret_cast<const float4*>(r + (((2 * c + 1) ^ sw) << 4));
+  }
+  if (n_left > 0) {
+    const int c = tid & 3;  // (kEpiWarps * 32 is a multiple of 4: the quarter index does not depend on q)
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      if (l >= n_left) break;
+      const float4 a0 = *reinterpret_cast<const float4*>(aleft + l * 32 + 8 * c);
+      const float4 a1 = *reinterpret_cast<const float4*>(aleft + l * 32 + 8 * c + 4);
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        float a = lacc[q][l];
+        a = fmaf(x[q][0].x, a0.x, a); a = fmaf(x[q][0].y, a0.y, a); a = fmaf(x[q][0].z, a0.z, a); a = fmaf(x[q][0].w, a0.w, a);
+        a = fmaf(x[q][1].x, a1.x, a); a = fmaf(x[q][1].y, a1.y, a); a = fmaf(x[q][1].z, a1.z, a); a = fmaf(x[q][1].w, a1.w, a);
+        lacc[q][l] = a;
+      }
+    }
   }
 #pragma unroll
   for (int q = 0; q < kPer; ++q) {
@@ -361,7 +386,7 @@ template <int kBlockT>
 __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CUtensorMap* tmP, int t_tile, int slot,
                                                    float* stage, uint64_t* bars, float* sh, int tid) {
   const FusedReduce& r = p.red;
-  EVC_CLK_DECL(c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_a = 0, c_w = 0);
+  EVC_CLK_DECL(c_0 = 0, c_1 = 0, c_2 = 0, c_3 = 0, c_a = 0, c_w = 0, c_left = 0, c_main = 0, c_tail = 0, c_bar = 0, c_iss = 0);
   EVC_CLK(c_0);
   // this CTA's batches of the tile: (2) below, after the tile barrier (1)
   const int g = tid >> 6, t64 = tid & 63;
@@ -376,7 +401,8 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
   const uint32_t bar0 = smem_u32(&bars[0]);
   float* s_left = sh + 16 * g;       // [8] leftover sums of frame g of the batch | [2] per-warp partials
   float* s_warp = s_left + 8;
-  auto issue = [&](int b, int s) {   // thread 0: box loads of batch b into slot s
+  const bool issuer = (tid == kEpiWarps * 32 - 1);  // a thread whose 64-thread group has the least other work
+  auto issue = [&](int b, int s) {   // one thread: box loads of batch b into slot s
     const int t = t_base + b * nb;
     float* dst = stage + (size_t)s * r.slot_floats;
     const uint32_t bar = bar0 + 8u * s;
@@ -408,7 +434,7 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
       const int fr = tid / c4, f = (tid - fr * c4) * 4;
       if (f < F_main) x_main = load_x4(tb + fr, f);
     }
-    if (g < nb && tb + g < p.T && F_main + t64 < r.F && r.left_rows > 0) x_tail = r.X[(size_t)(tb + g) * r.ldx + F_main + t64];
+    if (g < nb && tb + g < p.T && F_main + t64 < r.F && (r.left_rows > 0 || r.Lp)) x_tail = r.X[(size_t)(tb + g) * r.ldx + F_main + t64];
   };
   int b = slot, k = 0;
   uint32_t phases = 0;
@@ -441,7 +467,7 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
   named_bar_sync(1, kEpiWarps * 32);
   EVC_CLK(c_2);
 
-  if (tid == 0) {
+  if (issuer) {
     if (b < n_batches) issue(b, 0);
     if (r.nslots == 2 && b + r.contributors < n_batches) issue(b + r.contributors, 1);
   }
@@ -453,13 +479,20 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
     mbar_wait(bar0 + 8u * s, (phases >> s) & 1u);
     EVC_CLK_ADD(c_w, c_a);
     phases ^= 1u << s;
+    EVC_CLK(c_a);
     // leftover rows (the Nyquist bin): 64-thread group g sums frame g of the batch, in reduce_partials_kernel's order
     if (left_floats > 0 && g < nb) {
       const float* lst = st + (size_t)n_chunks * chunk_floats;
       for (int l = 0; l < r.n_left; ++l) {
         const float* row = lst + ((size_t)l * nb + g) * r.left_rows;
         float a = 0.f;
-        for (int q = t64; q < r.left_rows; q += kRedThreads) a += row[q];
+        for (int q0 = t64; q0 < r.left_rows; q0 += 8 * kRedThreads) {  // loads first, adds in order (same sum)
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (q0 + e * kRedThreads < r.left_rows) ? row[q0 + e * kRedThreads] : 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) if (q0 + e * kRedThreads < r.left_rows) a += v[e];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if ((t64 & 31) == 0) s_warp[t64 >> 5] = a;
@@ -468,6 +501,8 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
         named_bar_sync(2 + g, kRedThreads);
       }
     }
+    EVC_CLK_ADD(c_left, c_a);
+    EVC_CLK(c_a);
     // tensor-core columns: float4 per thread, splits summed in order (deterministic)
     const int c4_per_frame = ldp >> 2;
     for (int idx = tid, it = 0; idx < nb * c4_per_frame; idx += kEpiWarps * 32, ++it) {
@@ -478,9 +513,15 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
       const float4 x4 = (it == 0) ? x_main : load_x4(t, f);
       const float* src = st + (size_t)c * chunk_floats + (size_t)fr * kRedCols + (f - c * kRedCols);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int kk = 0; kk < n; ++kk) {
-        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)kk * nb * kRedCols);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      const size_t kstride = (size_t)nb * kRedCols;
+      for (int k0 = 0; k0 < n; k0 += 6) {  // six splits' loads in flight, added in split order
+        float4 v[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+          v[e] = (k0 + e < n) ? *reinterpret_cast<const float4*>(src + (size_t)(k0 + e) * kstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+          if (k0 + e < n) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
       }
       if (f + 3 < F_main) {  // whole group inside the tensor-core rows: vector stores
         if (f < r.ldwh) *reinterpret_cast<float4*>(r.WH + (size_t)t * r.ldwh + f) = acc;
@@ -498,26 +539,37 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
         }
       }
     }
+    EVC_CLK_ADD(c_main, c_a);
+    EVC_CLK(c_a);
+    const float x_tail_now = x_tail;
+    // this thread's X entries of the CTA's next batch, fetched under the rest of this batch and the next wait
+    prefetch_x(b + r.contributors);
     // columns past the tensor-core rows: the leftover rows, then zero padding
     if (g < nb && t_b + g < p.T) {
       const int t = t_b + g;
       for (int f = F_main + t64, it = 0; f < r.cols; f += kRedThreads, ++it) {
-        const bool have = f < r.F && r.left_rows > 0;
-        const float sum = have ? s_left[f - F_main] : 0.f;
+        const bool have = f < r.F && (r.left_rows > 0 || r.Lp);
+        float sum = 0.f;
+        if (have && r.Lp)
+          for (int kk = 0; kk < r.lp_splits; ++kk) sum += __ldcg(r.Lp + ((size_t)kk * r.n_left + (f - F_main)) * r.left_ld + t);
+        else if (have) sum = s_left[f - F_main];
         if (f < r.ldwh && (have || f >= r.F)) r.WH[(size_t)t * r.ldwh + f] = sum;
-        if (r.X) store_r(r.ro, t, f, have ? __fdiv_rn(it == 0 ? x_tail : r.X[(size_t)t * r.ldx + f], fmaxf(sum, p.eps)) : 0.f);
+        if (r.X) store_r(r.ro, t, f, have ? __fdiv_rn(it == 0 ? x_tail_now : r.X[(size_t)t * r.ldx + f], fmaxf(sum, p.eps)) : 0.f);
       }
     }
-    // this thread's X entries of the CTA's next batch, fetched under the barrier and the next wait
-    prefetch_x(b + r.contributors);
+    EVC_CLK_ADD(c_tail, c_a);
+    EVC_CLK(c_a);
     named_bar_sync(1, kEpiWarps * 32);  // the slot (and s_left) may be overwritten
+    EVC_CLK_ADD(c_bar, c_a);
+    EVC_CLK(c_a);
     const int bn = b + r.nslots * r.contributors;
-    if (tid == 0 && bn < n_batches) issue(bn, s);
+    if (issuer && bn < n_batches) issue(bn, s);
+    EVC_CLK_ADD(c_iss, c_a);
   }
   EVC_CLK(c_3);
   if (tid == 0)
-    EVC_CLK_PRINT(p, "clk cta %d fused reduce: fence %lld barrier %lld reduce %lld (waiting for copies %lld, %d batches)\n", (int)blockIdx.x,
-                  c_1 - c_0, c_2 - c_1, c_3 - c_2, c_w, k);
+    EVC_CLK_PRINT(p, "clk cta %d fused reduce: fence %lld barrier %lld reduce %lld (copies %lld left %lld main %lld tail %lld bar %lld issue %lld, %d batches)\n",
+                  (int)blockIdx.x, c_1 - c_0, c_2 - c_1, c_3 - c_2, c_w, c_left, c_main, c_tail, c_bar, c_iss, k);
 }
 
 // kP = CTA pairs per cluster.  With kP > 1 the pairs of a cluster work on items that share one operand tile -- the
@@ -568,8 +620,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     tma_prefetch_desc(&tmM);
     tma_prefetch_desc(&tmN);
     if (kStageH) tma_prefetch_desc(&tmH);
-    if (Cfg::kShadow) tma_prefetch_desc(&tmS);
-    if (kFro || (kEpi == TEPI_PARTIAL && p.red.enabled)) tma_prefetch_desc(&tmQ);
+    if (Cfg::kShadow || (kSplitN && p.n_left > 0)) tma_prefetch_desc(&tmS);
+    if (kFro || (kEpi == TEPI_PARTIAL && p.red.enabled == 1)) tma_prefetch_desc(&tmQ);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bar_full[i]), Cfg::kFullArrivals);
       mbar_init(smem_u32(&bar_raw[i]), 1);
@@ -663,8 +715,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             }
           if (kSplitN) {
             const uint32_t rawb = smem_u32(&bar_raw[stage]);
-            mbar_arrive_expect_tx(rawb, (uint32_t)Cfg::kRawBytes);
+            mbar_arrive_expect_tx(rawb, (uint32_t)(Cfg::kRawBytes + (p.n_left > 0 ? Cfg::kLeftBytes : 0)));
             tma_load_2d(sbase + Cfg::kOffRaw, &tmN, kc, t0, rawb, kEvictFirst);  // H is streamed: keep A^T in L2
+            // rows F_main.. of the transposed dictionary for this K-block (rows past n_left are zero-filled)
+            if (p.n_left > 0) tma_load_2d(sbase + Cfg::kOffLeft, &tmS, kc, 0, rawb, kEvictNormal);
           } else {
             constexpr int kNSlice = Cfg::kNRows / kP;
 #pragma unroll
@@ -826,17 +880,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
         // planes of the frame operand (the activations) from the fp32 tile TMA brought -- all 8 warps on every
         // stage, so every warp observes every phase of bar_raw
         const int tid = threadIdx.x - 64;
+        constexpr int kPer = Cfg::kNRows * 4 / (kEpiWarps * 32);
+        // the pairs of dictionary-row group 0 also carry the rows that stay off the tensor cores (same K range)
+        const int n_left = (m_group == 0) ? p.n_left : 0;
+        float lacc[kPer][8];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+#pragma unroll
+          for (int l = 0; l < 8; ++l) lacc[q][l] = 0.f;
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           EVC_CLK(c_a);
           mbar_wait(smem_u32(&bar_raw[stage]), phase);
           EVC_CLK_ADD(c_wraw, c_a);
           uint8_t* sb = ring_ptr + stage * Cfg::kStageBytes;
           if (!EVC_DBG(p, 1))
-            split_planes<Cfg::kNRows>(sb + Cfg::kOffRaw, sb + Cfg::kOffN, sb + Cfg::kOffN + Cfg::kNPlaneBytes, tid);
+            split_planes<Cfg::kNRows>(sb + Cfg::kOffRaw, sb + Cfg::kOffN, sb + Cfg::kOffN + Cfg::kNPlaneBytes, tid,
+                                      reinterpret_cast<const float*>(sb + Cfg::kOffLeft), n_left, lacc);
           fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma's operand reads
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(full_leader + (uint32_t)stage * 8u);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        // this split's share of (A H)[t, F_main + l]: the four quarter-row threads of a frame are adjacent lanes
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          if (l >= n_left) break;
+#pragma unroll
+          for (int q = 0; q < kPer; ++q) {
+            float v = lacc[q][l];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const int t = t0 + (int)rank * Cfg::kNRows + ((q * (kEpiWarps * 32) + tid) >> 2);
+            if ((tid & 3) == 0 && t < p.left_ld) p.left_out[((size_t)split * p.n_left + l) * p.left_ld + t] = v;
+          }
         }
       }
       EVC_CLK(c_a);
@@ -949,6 +1025,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           const uint32_t taddr =
               tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * kMTiles + i) * kBlockT + c * 32);
           tmem_ld_32x32(taddr, v);
+          if (p.red.enabled == 2) {
+            // K is not split: this accumulator IS A*H -- the ratio X / max(A H, eps) (and / or A*H itself) leaves
+            // straight from TMEM, no partials, no second pass (sklearn _nmf.py:554-571)
+            const FusedReduce& r = p.red;
+            float x[32];
+            if (r.X) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = (m_ok && tb + j < p.T) ? __ldg(r.X + (size_t)(tb + j) * r.ldx + m) : 0.f;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (!m_ok || tb + j >= p.T) continue;
+              const float sum = __uint_as_float(v[j]);
+              if (r.WH) r.WH[(size_t)(tb + j) * r.ldwh + m] = sum;
+              if (r.X) store_r(r.ro, tb + j, m, __fdiv_rn(x[j], fmaxf(sum, p.eps)));
+            }
+            continue;
+          }
           tmem_ld_wait();
           // whole chunk in range and every lane a real row: straight-line code
           const bool fast = (tb + 32 <= p.T) && rows_full;
@@ -968,7 +1063,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           }
         }
       }
-      if (kEpi == TEPI_PARTIAL && p.red.enabled) {
+      if (kEpi == TEPI_PARTIAL && p.red.enabled == 1) {
         // split-K sum (+ ratio) by the contraction's own CTAs; one item per pair in this mode, the ring is idle
         const int groups = p.splits_last ? p.num_m_groups - 1 : p.num_m_groups;
         const int idx = (item < p.items_main) ? w.m_group + groups * split : groups * p.num_splits + split;
@@ -1012,12 +1107,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 __global__ void __launch_bounds__(kRedThreads)
 reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
                        float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
-                       int left_ld, const float* __restrict__ X, int ldx, float eps, ROut ro, int batch) {
+                       int left_ld, const float* __restrict__ X, int ldx, float eps, ROut ro, int batch, int chunk0,
+                       const float* __restrict__ Lp, int lp_splits) {
   extern __shared__ __align__(128) float red_smem[];  // [batch][kRedCols] staged partials | [n_left][left_rows]
   __shared__ __align__(8) uint64_t bar;
   __shared__ float s_left[8];
   __shared__ float s_warp[kRedThreads / 32];
-  const int t = blockIdx.x, c0 = blockIdx.y * kRedCols;
+  const int t = blockIdx.x, c0 = ((int)blockIdx.y + chunk0) * kRedCols;  // chunk0 > 0: only the columns past the tensor-core rows
   float* stage = red_smem;
   float* lstage = red_smem + (size_t)batch * kRedCols;
   if (threadIdx.x == 0) {
@@ -1084,6 +1180,10 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
     float s = 0.f;
     bool have = false;
     if (f < F_main) { s = sv[j]; have = true; }
+    else if (f < F && Lp) {  // rows kept off the tensor cores: contraction 1's per-split sums [split][row][frame]
+      for (int k = 0; k < lp_splits; ++k) s += __ldcg(Lp + ((size_t)k * n_left + (f - F_main)) * left_ld + t);
+      have = true;
+    }
     else if (f < F && left_rows > 0) { s = s_left[f - F_main]; have = true; }
     if (f < ldwh && (have || f >= F)) WH[(size_t)t * ldwh + f] = s;
     if (X) {
@@ -1617,7 +1717,8 @@ inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, i
   if (mode == EVC_MODE_FP32) return EVC_OK;
   const C1Plan pl = c1_plan(o.F_main, o.N, T, mode);
   o.left_valid = false;
-  const size_t left = (size_t)left_rows(o, mode) * o.n_left * left_ld(T);
+  // leftover-row partials: one per 32 exemplars (fused update, fast modes) or one per K split (contraction 1)
+  const size_t left = (size_t)std::max(left_rows(o, mode), pl.max_splits) * o.n_left * left_ld(T);
   EVC_TRY(ws->reserve((ws_left_offset(pl, T) + left) * sizeof(float)));
   EVC_TRY(reserve_ratio(o, mode, T, s));
   if (mode == EVC_MODE_BF16) {
@@ -1664,9 +1765,18 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   p.m_plane_rows = (int)o.at_rows; p.n_plane_rows = 0;
   p.out = partials; p.ld_out = pl.ldp;
   p.out_keep_l2 = getenv("EVC_NO_KEEP_L2") ? 0 : 1;
-  // leftover rows: from the fused update's partials when they describe this H, else a dot-product pass over H
-  const bool from_partials = o.n_left > 0 && !target && o.left_valid;
-  const bool standalone = o.n_left > 0 && !from_partials;
+  // leftover rows (F_main..): in the fp32-accurate mode contraction 1's split warps carry them along (per-split sums
+  // in the workspace, summed with the partials); in the fast modes they come from the fused update's partials when
+  // those describe this H, else from a dot-product pass over H
+  const bool own_left = kSplitN && o.n_left > 0;
+  const bool from_partials = !own_left && o.n_left > 0 && !target && o.left_valid;
+  const bool standalone = !own_left && o.n_left > 0 && !from_partials;
+  const int lp_splits = (pl.splits_last && pl.m_groups == 1) ? pl.splits_last : pl.splits;  // of dictionary-row group 0
+  CUtensorMap tmL = tmH;
+  if (own_left) {
+    EVC_TRY(make_tmap(&tmL, target ? o.BTleft : o.ATleft, o.n_left, o.N, o.ldN, 32, 8, false));
+    p.n_left = o.n_left; p.left_out = leftp; p.left_ld = left_ld(T);
+  }
   const bool fuse = ra && !standalone;  // the ratio is formed in the same pass as the split-K sum
   const ROut ro = fuse ? ratio_out(o, mode, ra->R, ra->ldR) : ROut{};
   const int cols = std::max(ldWH, fuse ? ro.cols() : 0);
@@ -1674,10 +1784,15 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   // The sum (+ ratio) runs inside the contraction itself when every work item is resident at once (always the case
   // when K is split) and a unit's partials fit the staging slots the idle operand ring offers; else a second launch.
   using L1 = TcLaunch<kC1MTiles, kC1BlockT, kPrec, kSplitN, TEPI_PARTIAL, kP, true>;
-  bool in_kernel = false;
+  bool in_kernel = false, direct = false;
   CUtensorMap tmP = tmH;  // the partials as a (column, frame, split) tensor when the sum runs in the kernel
   {
+    // EVC_NO_FUSED_REDUCE=1: always the separate pass.  EVC_FUSED_REDUCE=1: also when K is split (tile barrier + sum
+    // by the contraction's own CTAs) -- bit-identical, but measured slower than the separate pass at the headline
+    // shape (74 us against 59 + 11 us: fence + tile barrier cost ~7k cycles and 256 threads per SM hide the copy and
+    // shared-memory latencies worse than eleven resident blocks of the reduction kernel), so it is not the default.
     static const bool allow = getenv("EVC_NO_FUSED_REDUCE") == nullptr;
+    static const bool allow_split = allow && getenv("EVC_FUSED_REDUCE") != nullptr && atoi(getenv("EVC_FUSED_REDUCE")) != 0;
     const int items = p.items_main + p.splits_last * p.num_t_tiles;
     const size_t ring_floats = (size_t)L1::Cfg::kStages * L1::Cfg::kStageBytes / sizeof(float);
     const int n_chunks = ceil_div(pl.ldp, kRedCols);
@@ -1689,17 +1804,26 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
         const size_t sf = round_up_sz((size_t)n_chunks * pl.max_splits * cand * kRedCols + (size_t)o.n_left * cand * lrows, 32);
         if (cand_slots * sf <= ring_floats) { nb = cand; nslots = cand_slots; slot_floats = sf; }
       }
-    if (allow && nb > 0 && items <= L1::slots() && pl.t_tiles * kP <= kRedMaxTiles && o.red_ctr.p && pl.max_splits <= 256) {
+    FusedReduce& r = p.red;
+    if (allow && pl.max_splits == 1 && o.F_main % kRedCols == 0) {
+      // K is not split (many frames): A*H is complete in TMEM -- the epilogue writes the ratio (with `ra`) or A*H
+      // (without) itself; the separate pass below only sees the columns past the tensor-core rows
+      direct = true;
+      r.enabled = 2;
+      r.WH = fuse ? nullptr : WH; r.ldwh = ldWH;  // nobody reads A*H of an iteration whose ratio is formed here
+      r.X = fuse ? ra->X : nullptr; r.ldx = fuse ? ra->ldX : 0; r.ro = ro;
+      p.eps = fuse ? ra->eps : 0.f;
+    } else if (allow_split && nb > 0 && items <= L1::slots() && pl.t_tiles * kP <= kRedMaxTiles && o.red_ctr.p && pl.max_splits <= 256) {
       in_kernel = true;
       EVC_TRY(make_tmap3d(&tmP, partials, pl.ldp, T, pl.max_splits, (size_t)pl.ldp, (size_t)T * pl.ldp, kRedCols, nb,
                           pl.max_splits));
-      FusedReduce& r = p.red;
       r.enabled = 1; r.counter = o.red_ctr.as<unsigned int>();
       r.contributors = ((pl.splits_last ? pl.m_groups - 1 : pl.m_groups) * pl.splits + pl.splits_last) * kCG;
       r.nslots = nslots; r.nb = nb; r.slot_floats = (int)slot_floats;
       r.S = pl.splits; r.S_last = pl.splits_last; r.f_last = pl.f_last; r.F = o.F;
       r.WH = WH; r.ldwh = ldWH;
       r.L = leftp; r.left_rows = lrows; r.left_ld = left_ld(T); r.n_left = o.n_left;
+      r.Lp = own_left ? leftp : nullptr; r.lp_splits = lp_splits;
       r.X = fuse ? ra->X : nullptr; r.ldx = fuse ? ra->ldX : 0;
       r.cols = cols; r.ro = ro;
       p.eps = fuse ? ra->eps : 0.f;
@@ -1710,9 +1834,9 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
     const CUtensorMap& tmD = (kPrec == PREC_TF32) ? (target ? o.tmBT : o.tmAT)
                              : (kP == 1)          ? (target ? o.tmBT16 : o.tmAT16)
                                                   : (target ? o.tmBT16_s[kP / 4] : o.tmAT16_s[kP / 4]);
-    EVC_TRY((L1::launch(tmD, tmH, tmH, tmP, tmH, p, s)));
+    EVC_TRY((L1::launch(tmD, tmH, tmH, tmP, tmL, p, s)));
   }
-  if (!in_kernel) {
+  if (!in_kernel && !(direct && ceil_div(cols, kRedCols) <= o.F_main / kRedCols)) {
     ProfScope ps(1, s);
     const int batch = std::max(1, std::min(kRedMaxBatch, pl.max_splits));
     const size_t smem = ((size_t)batch * kRedCols + (size_t)o.n_left * lrows) * sizeof(float);
@@ -1724,15 +1848,18 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     if (smem > 160 * 1024) return fail(EVC_ERR_UNSUPPORTED, "split-K reduction: %zu bytes of staging exceed shared memory", smem);
+    // (after the direct epilogue: only the column chunks past the tensor-core rows -- leftover rows and zero padding)
+    const int chunk0 = direct ? o.F_main / kRedCols : 0;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(T, ceil_div(cols, kRedCols)); cfg.blockDim = dim3(kRedThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(T, ceil_div(cols, kRedCols) - chunk0); cfg.blockDim = dim3(kRedThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
     EVC_CUDA(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, (const float*)partials, pl.splits, pl.splits_last, pl.f_last, T,
                                 pl.ldp, o.F, o.F_main, WH, ldWH, (const float*)leftp, lrows, o.n_left, left_ld(T),
-                                fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0, fuse ? ra->eps : 0.f, ro, batch));
+                                fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0, fuse ? ra->eps : 0.f, ro, batch, chunk0,
+                                own_left ? (const float*)leftp : (const float*)nullptr, lp_splits));
     EVC_LAUNCH_CHECK();
   }
   if (standalone) {
@@ -1820,7 +1947,7 @@ inline int contract2_t(DictOperands& o, int mode, int T, const float* R, int ldR
 }
 
 inline void left_args(DictOperands& o, int mode, int T, DevBuf* ws, GemmParams& p) {
-  if (o.n_left <= 0) return;
+  if (o.n_left <= 0 || mode == EVC_MODE_3XTF32) return;  // (fp32-accurate mode: contraction 1 carries those rows itself)
   const C1Plan pl = c1_plan(o.F_main, o.N, T, mode);
   p.left_a = (mode == EVC_MODE_TF32) ? o.AT + (size_t)o.F_main * o.ldN : o.ATleft;
   p.left_lda = o.ldN; p.n_left = o.n_left;

@@ -1,6 +1,7 @@
 """Digest of a short solve at several shapes, for comparing two builds / environments bit for bit:
-    python tests/manual/fused_reduce_ab.py            (split-K sum + ratio inside contraction 1, the default)
-    EVC_NO_FUSED_REDUCE=1 python tests/manual/fused_reduce_ab.py   (the separate reduce_partials_kernel launch)
+    EVC_FUSED_REDUCE=1 python tests/manual/fused_reduce_ab.py      (split-K sum + ratio inside contraction 1 at every
+                                                                    shape; without the variable only where K is not split)
+    EVC_NO_FUSED_REDUCE=1 python tests/manual/fused_reduce_ab.py   (always the separate reduce_partials_kernel launch)
 Both must print identical lines: the in-kernel pass sums the partials in the same order (sklearn _nmf.py:554-571)."""
 import hashlib
 import os

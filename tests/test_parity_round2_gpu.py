@@ -219,17 +219,18 @@ def test_content_keyed_cache_is_used_and_never_stale(tmp_path):
 
 def test_in_kernel_split_k_sum_equals_the_separate_reduction_pass():
     """The split-K sum + ratio done by contraction 1's own CTAs (the first GEMM's epilogue, sklearn _nmf.py:554-571)
-    gives bit for bit the results of the separate reduce_partials_kernel launch it replaces (EVC_NO_FUSED_REDUCE=1),
-    at six shapes (split-K with and without leftover rows, several row groups, no split at T = 19000) in all three
-    tensor-core modes.  The switch is read once per process, so each variant runs in its own interpreter."""
+    gives bit for bit the results of the separate reduce_partials_kernel launch (EVC_NO_FUSED_REDUCE=1), at six shapes
+    (split-K with and without leftover rows, several row groups; at T = 19000 K is not split and the ratio leaves
+    straight from TMEM, the default there) in all three tensor-core modes.  EVC_FUSED_REDUCE=1 turns the in-kernel sum
+    on for the split-K shapes too (it is not the default: measured slower than the separate pass).  The switch is read once per process, so each variant runs in its own interpreter."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = os.path.join(root, "tests", "manual", "fused_reduce_ab.py")
     outs = []
-    for extra in ({}, {"EVC_NO_FUSED_REDUCE": "1"}):
-        env = dict(os.environ, **extra)
-        env.pop("EVC_NO_FUSED_REDUCE", None) if not extra else None
+    for extra in ({"EVC_FUSED_REDUCE": "1"}, {"EVC_NO_FUSED_REDUCE": "1"}):
+        env = {k: v for k, v in os.environ.items() if k not in ("EVC_FUSED_REDUCE", "EVC_NO_FUSED_REDUCE")}
+        env.update(extra)
         r = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append([l for l in r.stdout.splitlines() if " H " in l])
