@@ -1105,7 +1105,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 // 256 columns x 64 threads per block: 18 KB of staging at the headline shape, so eleven blocks share an SM and the
 // 3 000 blocks of a launch run in under two waves (512 columns: five per SM, 2.7 waves, 17.6 us -- profiles/r2_ncu_summary.txt).
 __global__ void __launch_bounds__(kRedThreads)
-reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
+reduce_partials_kernel(const __grid_constant__ CUtensorMap tmP,  // P as a (column, frame, split) tensor, boxes 256 x 1 x batch
+                       const float* __restrict__ P, int S, int S_last, int f_last, int T, int ldp, int F, int F_main,
                        float* __restrict__ WH, int ldwh, const float* __restrict__ L, int left_rows, int n_left,
                        int left_ld, const float* __restrict__ X, int ldx, float eps, ROut ro, int batch, int chunk0,
                        const float* __restrict__ Lp, int lp_splits) {
@@ -1117,29 +1118,33 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
   float* stage = red_smem;
   float* lstage = red_smem + (size_t)batch * kRedCols;
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmP);
     mbar_init(smem_u32(&bar), 1);
     fence_barrier_init();
   }
-  __syncthreads();
-  pdl_wait();
-  pdl_launch_dependents();
   const int pcols = max(0, min(kRedCols, min(ldp, F_main) - c0));  // tensor-core columns of this chunk (a multiple of 4)
   const int pcols_ld = max(0, min(kRedCols, ldp - c0));             // ... including the partial buffer's pad columns
   const int n = (c0 >= f_last) ? S_last : S;                        // the last row group has its own split count
   const bool has_left = left_rows > 0 && F_main >= c0 && F_main < c0 + kRedCols;
+  const int col = threadIdx.x * 4;  // this thread's 4 columns of the chunk
+  // the frame's X entries do not depend on the kernel before this one: in flight across the dependency wait
+  const bool x_vec = X && col < pcols && c0 + col + 3 < F_main && (ldx & 3) == 0 && (((uintptr_t)X) & 15) == 0;
+  float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x_vec) x4 = __ldg(reinterpret_cast<const float4*>(X + (size_t)t * ldx + c0 + col));
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
   uint32_t phase = 0;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int col = threadIdx.x * 4;  // this thread's 4 columns of the chunk
   for (int k0 = 0; k0 < n || (k0 == 0 && has_left); k0 += batch) {
     const int nb = max(0, min(batch, n - k0));
     if (threadIdx.x == 0) {
-      uint32_t bytes = (pcols_ld > 0 ? (uint32_t)nb * pcols_ld * 4u : 0u);
+      // ONE box load brings the chunk's rows of all `batch` splits (per-split 1 KB bulk copies were bound by their
+      // issue rate); splits / columns past the tensor are zero-filled and still counted
+      uint32_t bytes = (pcols_ld > 0 && nb > 0) ? (uint32_t)batch * kRedCols * 4u : 0u;
       if (k0 == 0 && has_left) bytes += (uint32_t)n_left * left_rows * 4u;
       mbar_arrive_expect_tx(smem_u32(&bar), bytes);
-      if (pcols_ld > 0)
-        for (int k = 0; k < nb; ++k)
-          bulk_load_1d(smem_u32(stage + (size_t)k * kRedCols), P + ((size_t)(k0 + k) * T + t) * ldp + c0,
-                       (uint32_t)pcols_ld * 4u, smem_u32(&bar), kEvictFirst);
+      if (pcols_ld > 0 && nb > 0) tma_load_3d(smem_u32(stage), &tmP, c0, t, k0, smem_u32(&bar), kEvictFirst);
       if (k0 == 0 && has_left)
         for (int l = 0; l < n_left; ++l)
           bulk_load_1d(smem_u32(lstage + (size_t)l * left_rows), L + ((size_t)l * left_ld + t) * left_rows,
@@ -1148,9 +1153,14 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
     mbar_wait(smem_u32(&bar), phase);
     phase ^= 1u;
     if (col < pcols)
-      for (int k = 0; k < nb; ++k) {  // split order: deterministic
-        const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)k * kRedCols + col);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      for (int kq = 0; kq < nb; kq += 6) {  // six splits' loads in flight, added in split order: deterministic
+        float4 v[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+          v[e] = (kq + e < nb) ? *reinterpret_cast<const float4*>(stage + (size_t)(kq + e) * kRedCols + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 6; ++e)
+          if (kq + e < nb) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
       }
     if (k0 == 0 && has_left) {
       for (int l = 0; l < n_left; ++l) {
@@ -1173,6 +1183,15 @@ reduce_partials_kernel(const float* __restrict__ P, int S, int S_last, int f_las
   }
   const float sv[4] = {acc.x, acc.y, acc.z, acc.w};
   const int cols = max(ldwh, X ? ro.cols() : 0);
+  if (c0 + col + 3 < F_main && (!X || x_vec) && (ldwh & 3) == 0 && (((uintptr_t)WH) & 15) == 0) {
+    // four tensor-core columns: vector stores
+    const int f = c0 + col;
+    if (f < ldwh) *reinterpret_cast<float4*>(WH + (size_t)t * ldwh + f) = acc;
+    if (X)
+      store_r4(ro, t, f, make_float4(__fdiv_rn(x4.x, fmaxf(acc.x, eps)), __fdiv_rn(x4.y, fmaxf(acc.y, eps)),
+                                     __fdiv_rn(x4.z, fmaxf(acc.z, eps)), __fdiv_rn(x4.w, fmaxf(acc.w, eps))));
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int f = c0 + col + j;
@@ -1856,7 +1875,9 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
-    EVC_CUDA(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, (const float*)partials, pl.splits, pl.splits_last, pl.f_last, T,
+    CUtensorMap tmPb;
+    EVC_TRY(make_tmap3d(&tmPb, partials, pl.ldp, T, pl.max_splits, (size_t)pl.ldp, (size_t)T * pl.ldp, kRedCols, 1, batch));
+    EVC_CUDA(cudaLaunchKernelEx(&cfg, reduce_partials_kernel, tmPb, (const float*)partials, pl.splits, pl.splits_last, pl.f_last, T,
                                 pl.ldp, o.F, o.F_main, WH, ldWH, (const float*)leftp, lrows, o.n_left, left_ld(T),
                                 fuse ? ra->X : (const float*)nullptr, fuse ? ra->ldX : 0, fuse ? ra->eps : 0.f, ro, batch, chunk0,
                                 own_left ? (const float*)leftp : (const float*)nullptr, lp_splits));
