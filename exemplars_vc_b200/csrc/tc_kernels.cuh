@@ -607,7 +607,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_red[2];          // FusedReduce: the partials of a batch landed (one per slot)
   __shared__ float red_sh[64];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform: role branches do not diverge
   const int lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const uint32_t rank = crank & 1u;         // rank inside the CTA pair: 0 = leader (issues the MMAs)
@@ -677,7 +677,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
 
   if (warp == 0) {
     // ================= TMA producer (one thread in each CTA of the pair) =================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wait = 0);
@@ -738,7 +738,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA of the pair only) =================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wacc = 0, c_wfull = 0);
@@ -798,7 +798,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp) {
     // ================= H chunk loader: prefetches the activations the epilogue will update =================
-    if (lane == 0) {
+    if (elect_one()) {
       int hbase = 0;
       EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wait = 0);
       EVC_CLK(c_t0);
@@ -829,7 +829,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
     }
   } else if (kStageH && warp == Cfg::kLoaderWarp + 1) {
     // ================= H chunk storer =================
-    if (lane == 0 && !(p.direct_store && !Cfg::kShadow)) {
+    if (!(p.direct_store && !Cfg::kShadow) && elect_one()) {
       int hbase = 0;
       EVC_CLK_DECL(c_t0 = 0, c_a = 0, c_wait = 0, c_wread = 0);
       EVC_CLK(c_t0);

@@ -56,6 +56,19 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// One lane of a converged warp.  Single-thread role loops are entered through this (not `lane == 0`): the compiler
+// then knows exactly one thread is active, keeps the loop's addresses / descriptors in uniform registers and issues
+// UTCHMMA / UTMALDG directly -- behind `lane == 0` every such instruction sat in an ELECT + 7 x R2UR "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- thread-block clusters / CTA pairs ------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
