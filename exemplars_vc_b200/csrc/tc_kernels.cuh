@@ -27,7 +27,8 @@
 //   PREC_BF16   (EVC_MODE_BF16): one kind::f16 MMA per product on bf16 copies (dictionary converted once, the ratio
 //               emitted in bf16, a bf16 shadow of H kept by the fused update).
 //
-// A K-block is one swizzle row: 32 elements (64-byte bf16 rows, two planes) in PREC_SPLIT, 32 fp32 or 64 bf16
+// A K-block is one 128-byte swizzle row: 32 elements in PREC_SPLIT (their 32 hi and 32 lo bf16 values side by side:
+// "interleaved planes", one TMA box with full 128-byte row segments brings both), 32 fp32 or 64 bf16
 // (128-byte rows) in the fast modes; one MMA advances 32 bytes of K.
 //
 // CTA pairs: M = 256 (128 rows per CTA), N = 256 with the frame operand split in halves between the two CTAs'
@@ -51,6 +52,10 @@ using namespace umma;
 // profiles/r2_pitch_before_fix_ncu.txt).
 inline int k_pitch(int F) { return round_up(F, 32); }
 inline int k_pitch16(int F) { return round_up(F, 64); }
+// ... and of an operand with interleaved hi / lo planes (fp32-accurate mode): per 32 K elements, 32 hi then 32 lo bf16
+// values -- one 128-byte row segment per K-block; element k of plane p sits at column (k / 32) * 64 + p * 32 + k % 32.
+inline int k_pitch_i(int K) { return 2 * round_up(K, 32); }
+__host__ __device__ __forceinline__ int col_i(int k) { return ((k >> 5) << 6) + (k & 31); }
 
 enum TcEpilogue { TEPI_PARTIAL = 0, TEPI_MU_KL = 1, TEPI_MU_FRO = 2 };
 enum TcPrec { PREC_SPLIT = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
@@ -71,16 +76,17 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 struct ROut {
   float* R; int ldr;
   __nv_bfloat16* R16; int ldr16;
-  __nv_bfloat16* R12; int ldr12; size_t plane;
-  __host__ __device__ int cols() const { return R12 ? ldr12 : (R16 ? ldr16 : (R ? ldr : 0)); }
+  __nv_bfloat16* R12; int ldr12, k12;  // interleaved planes: pitch, logical columns (F rounded up to whole K-blocks)
+  __host__ __device__ int cols() const { return R12 ? k12 : (R16 ? ldr16 : (R ? ldr : 0)); }
 };
 __device__ __forceinline__ void store_r(const ROut& o, int t, int f, float r) {
   if (o.R && f < o.ldr) o.R[(size_t)t * o.ldr + f] = r;
   if (o.R16 && f < o.ldr16) o.R16[(size_t)t * o.ldr16 + f] = __float2bfloat16_rn(r);
-  if (o.R12 && f < o.ldr12) {
+  if (o.R12 && f < o.k12) {
     const __nv_bfloat16 r1 = __float2bfloat16_rn(r);
-    o.R12[(size_t)t * o.ldr12 + f] = r1;
-    o.R12[o.plane + (size_t)t * o.ldr12 + f] = __float2bfloat16_rn(r - __bfloat162float(r1));
+    __nv_bfloat16* q = o.R12 + (size_t)t * o.ldr12 + col_i(f);
+    q[0] = r1;
+    q[32] = __float2bfloat16_rn(r - __bfloat162float(r1));
   }
 }
 // four consecutive columns f..f+3 (f a multiple of 4, every pitch a multiple of 4): 8- / 16-byte stores
@@ -91,12 +97,13 @@ __device__ __forceinline__ void store_r4(const ROut& o, int t, int f, float4 r) 
     v.x = pack_bf16(r.x, r.y); v.y = pack_bf16(r.z, r.w);
     *reinterpret_cast<uint2*>(o.R16 + (size_t)t * o.ldr16 + f) = v;
   }
-  if (o.R12 && f < o.ldr12) {
+  if (o.R12 && f < o.k12) {
     uint2 hi, lo;
     split2(r.x, r.y, hi.x, lo.x);
     split2(r.z, r.w, hi.y, lo.y);
-    *reinterpret_cast<uint2*>(o.R12 + (size_t)t * o.ldr12 + f) = hi;
-    *reinterpret_cast<uint2*>(o.R12 + o.plane + (size_t)t * o.ldr12 + f) = lo;
+    __nv_bfloat16* q = o.R12 + (size_t)t * o.ldr12 + col_i(f);
+    *reinterpret_cast<uint2*>(q) = hi;
+    *reinterpret_cast<uint2*>(q + 32) = lo;
   }
 }
 
@@ -139,9 +146,6 @@ struct GemmParams {
   // kBlockT/2 frames each) so the last, partly filled round costs half a tile time.  half_from = items_main: off.
   int half_from;
   int m_fastest;  // work-item order: 1 = consecutive CTA pairs take consecutive dictionary-row groups of one frame tile
-  // PREC_SPLIT: the two bf16 planes of an operand are stacked along the row dimension of ONE tensor map; plane 1
-  // starts at row m_plane_rows (dictionary side) / n_plane_rows (frame side).
-  int m_plane_rows, n_plane_rows;
   float* out;    // PARTIAL: [split][t][m] with pitch ld_out;  MU_*: the activations H (T, ld_out)
   int ld_out;
   const float* colsum;
@@ -250,16 +254,25 @@ constexpr int kHChunkT = 32, kHBufBytes = kHChunkT * 128 * 4, kHBufs = EVC_H_BUF
 
 template <int kMTiles, int kBlockT, int kPrec, bool kSplitN, bool kStageH, bool kStageQ>
 struct TileCfg {
-  static constexpr int kRowBytes = (kPrec == PREC_SPLIT) ? 64 : 128;     // one K-block = one swizzle row
+  // One K-block = one 128-byte swizzle row of every operand that TMA brings: 32 fp32 (tf32), 64 bf16 (bf16), or -- in
+  // the fp32-accurate split mode -- the 32 hi and the 32 lo bf16 values of 32 K elements side by side ("interleaved
+  // planes": [hi 0..31 | lo 0..31]), so one box with full 128-byte row segments brings both planes (separate 64-byte
+  // rows per plane capped what an SM ingests at ~55 B/clk against ~85 with 128-byte rows: tools/probe/tma_issue_probe.cu).
+  // Only the frame operand that contraction 1 derives in shared memory (kSplitN) keeps two 64-byte-row planes.
   static constexpr int kPlanes = (kPrec == PREC_SPLIT) ? 2 : 1;
   static constexpr int kElemBytes = (kPrec == PREC_TF32) ? 4 : 2;
-  static constexpr int kKE = kRowBytes / kElemBytes;                     // K elements per K-block: 32 / 32 / 64
+  static constexpr int kKE = (kPrec == PREC_BF16) ? 64 : 32;             // K elements per K-block: 32 / 32 / 64
   static constexpr int kKStep = 32 / kElemBytes;                         // K elements per MMA: 16 / 8 / 16
-  static constexpr int kMPlaneBytes = 128 * kRowBytes;                   // this CTA's 128 rows of one sub-tile, one plane
-  static constexpr int kMBytes = kMTiles * kPlanes * kMPlaneBytes;
+  static constexpr int kBoxCols = 128 / kElemBytes;                      // tensor-map columns of one K-block: 64 / 32 / 64
+  static constexpr int kMRowBytes = 128;
+  static constexpr int kMSubBytes = 128 * kMRowBytes;                    // this CTA's 128 rows of one sub-tile (both planes)
+  static constexpr int kMBytes = kMTiles * kMSubBytes;
+  static constexpr int kMPlaneOff = 64;                                  // split mode: lo values start 64 bytes into the row
   static constexpr int kNRows = kBlockT / kCG;                           // frame rows this CTA holds
-  static constexpr int kNPlaneBytes = kNRows * kRowBytes;
-  static constexpr int kNBytes = kPlanes * kNPlaneBytes;
+  static constexpr int kNRowBytes = kSplitN ? 64 : 128;
+  static constexpr int kNPlaneBytes = kNRows * kNRowBytes;               // kSplitN: one derived plane
+  static constexpr int kNBytes = kSplitN ? 2 * kNPlaneBytes : kNRows * 128;
+  static constexpr int kNPlaneOff = kSplitN ? kNPlaneBytes : 64;         // where the lo plane starts (split mode)
   static constexpr int kRawBytes = kSplitN ? kNRows * 128 : 0;           // fp32 frame tile the planes are derived from
   // kSplitN: this K-block of the dictionary rows that stay off the tensor cores (F_main.., at most 8): [8][32] fp32
   static constexpr int kLeftBytes = kSplitN ? 8 * 128 : 0;
@@ -701,18 +714,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
           // the leader expects both CTAs' bytes (boxes past the matrix edge are zero-filled and still counted)
           if (rank == 0) mbar_arrive_expect_tx(smem_u32(&bar_full[stage]), (uint32_t)(kCG * Cfg::kTxBytes));
           const uint32_t sbase = ring + stage * Cfg::kStageBytes;
-          const int kc = kb * Cfg::kKE;
+          const int kc = kb * Cfg::kKE;        // K element / column of the fp32 tiles
+          const int kcb = kb * Cfg::kBoxCols;  // tensor-map column of the K-block's box
 #pragma unroll
-          for (int i = 0; i < kMTiles; ++i)
-#pragma unroll
-            for (int pl = 0; pl < Cfg::kPlanes; ++pl) {
-              const uint32_t dst = sbase + (i * Cfg::kPlanes + pl) * Cfg::kMPlaneBytes;
-              const int row = pl * p.m_plane_rows + m0 + i * Cfg::kRowsPerSub;
-              if (kP > 1 && kShareM)
-                tma_load_2d_pair_mc(dst + q * kSlice * Cfg::kRowBytes, &tmM, kc, row + q * kSlice, full, mc_mask, kEvictNormal);
-              else
-                tma_load_2d_pair(dst, &tmM, kc, row, full, kEvictNormal);
-            }
+          for (int i = 0; i < kMTiles; ++i) {
+            const uint32_t dst = sbase + i * Cfg::kMSubBytes;
+            const int row = m0 + i * Cfg::kRowsPerSub;
+            if (kP > 1 && kShareM)
+              tma_load_2d_pair_mc(dst + q * kSlice * Cfg::kMRowBytes, &tmM, kcb, row + q * kSlice, full, mc_mask, kEvictNormal);
+            else
+              tma_load_2d_pair(dst, &tmM, kcb, row, full, kEvictNormal);
+          }
           if (kSplitN) {
             const uint32_t rawb = smem_u32(&bar_raw[stage]);
             mbar_arrive_expect_tx(rawb, (uint32_t)(Cfg::kRawBytes + (p.n_left > 0 ? Cfg::kLeftBytes : 0)));
@@ -721,15 +733,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             if (p.n_left > 0) tma_load_2d(sbase + Cfg::kOffLeft, &tmS, kc, 0, rawb, kEvictNormal);
           } else {
             constexpr int kNSlice = Cfg::kNRows / kP;
-#pragma unroll
-            for (int pl = 0; pl < Cfg::kPlanes; ++pl) {
-              const uint32_t dst = sbase + Cfg::kOffN + pl * Cfg::kNPlaneBytes;
-              const int row = pl * p.n_plane_rows + t0;
-              if (kP > 1 && !kShareM)
-                tma_load_2d_pair_mc(dst + q * kNSlice * Cfg::kRowBytes, &tmN, kc, row + q * kNSlice, full, mc_mask, kEvictNormal);
-              else
-                tma_load_2d_pair(dst, &tmN, kc, row, full, kEvictNormal);
-            }
+            const uint32_t dst = sbase + Cfg::kOffN;
+            if (kP > 1 && !kShareM)
+              tma_load_2d_pair_mc(dst + q * kNSlice * 128, &tmN, kcb, t0 + q * kNSlice, full, mc_mask, kEvictNormal);
+            else
+              tma_load_2d_pair(dst, &tmN, kcb, t0, full, kEvictNormal);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -766,15 +774,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
             if (m0 + i * Cfg::kRowsPerSub >= p.M_total) break;  // pure padding: no MMAs, the epilogue skips it too
             if (EVC_DBG(p, 2)) break;
             const uint32_t d = tmem_base + (uint32_t)((acc * kMTiles + i) * kBlockT);
-            const uint32_t abase = sbase + i * Cfg::kPlanes * Cfg::kMPlaneBytes;
+            const uint32_t abase = sbase + i * Cfg::kMSubBytes;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t accum = (kb > kb0 || ks > 0) ? 1u : 0u;
-              const uint64_t a1 = make_smem_desc(abase + ks * 32, Cfg::kRowBytes);
-              const uint64_t b1 = make_smem_desc(nbase + ks * 32, Cfg::kRowBytes);
+              const uint64_t a1 = make_smem_desc(abase + ks * 32, Cfg::kMRowBytes);
+              const uint64_t b1 = make_smem_desc(nbase + ks * 32, Cfg::kNRowBytes);
               if (kPrec == PREC_SPLIT) {
                 // small terms first, then the leading one
-                const uint64_t a2 = make_smem_desc(abase + Cfg::kMPlaneBytes + ks * 32, Cfg::kRowBytes);
-                const uint64_t b2 = make_smem_desc(nbase + Cfg::kNPlaneBytes + ks * 32, Cfg::kRowBytes);
+                const uint64_t a2 = make_smem_desc(abase + Cfg::kMPlaneOff + ks * 32, Cfg::kMRowBytes);
+                const uint64_t b2 = make_smem_desc(nbase + Cfg::kNPlaneOff + ks * 32, Cfg::kNRowBytes);
                 mma_f16_2cta(d, a2, b1, idesc, accum);
                 mma_f16_2cta(d, a1, b2, idesc, 1u);
                 mma_f16_2cta(d, a1, b1, idesc, 1u);
@@ -1285,22 +1293,28 @@ __global__ void ratio_pad_kernel(const float* __restrict__ X, int ldx, const flo
 }
 
 // dst (rows, ldd) bf16 = src (rows, lds) fp32, round to nearest even; pad columns [cols, ldd) are zeroed.
-// With `plane` > 0 the second plane dst[plane + ...] = bf16_rn(src - bf16_rn(src)) is written too.
+// With `interleave` the destination holds both planes of the fp32-accurate split, x1 = bf16_rn(x) and
+// x2 = bf16_rn(x - x1), side by side per 32 columns (k_pitch_i / col_i).
 __global__ void to_bf16_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd,
-                               int rows, int cols, size_t plane) {
+                               int rows, int cols, int interleave) {
   const int r = blockIdx.x;
   const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-  if (r >= rows || c0 >= ldd) return;
+  const int lcols = interleave ? ldd / 2 : ldd;  // logical columns
+  if (r >= rows || c0 >= lcols) return;
   const float* sp = src + (size_t)r * lds;
   __nv_bfloat16* dp = dst + (size_t)r * ldd;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = c0 + j;
-    if (c >= ldd) break;
+    if (c >= lcols) break;
     const float x = c < cols ? sp[c] : 0.f;
     const __nv_bfloat16 x1 = __float2bfloat16_rn(x);
-    dp[c] = x1;
-    if (plane) dp[plane + c] = __float2bfloat16_rn(x - __bfloat162float(x1));
+    if (interleave) {
+      dp[col_i(c)] = x1;
+      dp[col_i(c) + 32] = __float2bfloat16_rn(x - __bfloat162float(x1));
+    } else {
+      dp[c] = x1;
+    }
   }
 }
 
@@ -1533,13 +1547,12 @@ struct DictOperands {
   }
 };
 
-// dst planes (bf16) <- src fp32 (rows, lds); `planes` = 1 or 2; the whole destination is zeroed first so pad rows
-// and pad columns are zero.
-inline int launch_to_bf16(const float* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols, size_t plane,
+// dst (bf16, or interleaved hi / lo planes) <- src fp32 (rows, lds); the destination was zeroed, so pad rows are zero.
+inline int launch_to_bf16(const float* src, int lds, __nv_bfloat16* dst, int ldd, int rows, int cols, bool interleave,
                           cudaStream_t s) {
   if (rows <= 0) return EVC_OK;
-  dim3 g(rows, ceil_div(ldd, 4 * 256));
-  to_bf16_kernel<<<g, 256, 0, s>>>(src, lds, dst, ldd, rows, cols, plane);
+  dim3 g(rows, ceil_div(interleave ? ldd / 2 : ldd, 4 * 256));
+  to_bf16_kernel<<<g, 256, 0, s>>>(src, lds, dst, ldd, rows, cols, interleave ? 1 : 0);
   EVC_LAUNCH_CHECK();
   return EVC_OK;
 }
@@ -1580,28 +1593,30 @@ inline int build_operands(DictOperands* o, int mode, const float* A, const float
     if (B) EVC_TRY(make_tmap(&o->tmBT, o->BT, o->F_main, N, o->ldN, 32, 128));
     return EVC_OK;
   }
-  const int planes = (mode == EVC_MODE_3XTF32) ? 2 : 1;
-  const int bk = bk_elems(mode);
-  o->ldA16 = k_pitch16(F); o->ldN16 = k_pitch16(N);
+  // 16-bit operands: bf16 copies (bf16 mode) or interleaved hi / lo planes (fp32-accurate mode); either way one
+  // K-block is 64 tensor-map columns = one 128-byte row segment
+  const bool il = (mode == EVC_MODE_3XTF32);
+  o->ldA16 = il ? k_pitch_i(F) : k_pitch16(F); o->ldN16 = il ? k_pitch_i(N) : k_pitch16(N);
   o->a_rows = plane_rows(N); o->at_rows = plane_rows(o->F_main);
   const size_t a_elems = (size_t)o->a_rows * o->ldA16, at_elems = (size_t)o->at_rows * o->ldN16;
-  EVC_CUDA(cudaMalloc(&o->A16, planes * a_elems * sizeof(__nv_bfloat16)));
-  EVC_CUDA(cudaMalloc(&o->AT16, planes * at_elems * sizeof(__nv_bfloat16)));
-  EVC_CUDA(cudaMemsetAsync(o->A16, 0, planes * a_elems * sizeof(__nv_bfloat16), s));
-  EVC_CUDA(cudaMemsetAsync(o->AT16, 0, planes * at_elems * sizeof(__nv_bfloat16), s));
-  EVC_TRY(launch_to_bf16(A, ldA, o->A16, o->ldA16, N, F, planes == 2 ? a_elems : 0, s));
-  EVC_TRY(launch_to_bf16(o->AT, o->ldN, o->AT16, o->ldN16, o->F_main, N, planes == 2 ? at_elems : 0, s));
-  EVC_TRY(make_tmap16(&o->tmA16, o->A16, planes * o->a_rows, F, o->ldA16, bk, 128));
-  EVC_TRY(make_tmap16(&o->tmAT16, o->AT16, planes * o->at_rows, N, o->ldN16, bk, 128));
-  EVC_TRY(make_tmap16(&o->tmAT16_s[0], o->AT16, planes * o->at_rows, N, o->ldN16, bk, 64));
-  EVC_TRY(make_tmap16(&o->tmAT16_s[1], o->AT16, planes * o->at_rows, N, o->ldN16, bk, 32));
+  EVC_CUDA(cudaMalloc(&o->A16, a_elems * sizeof(__nv_bfloat16)));
+  EVC_CUDA(cudaMalloc(&o->AT16, at_elems * sizeof(__nv_bfloat16)));
+  EVC_CUDA(cudaMemsetAsync(o->A16, 0, a_elems * sizeof(__nv_bfloat16), s));
+  EVC_CUDA(cudaMemsetAsync(o->AT16, 0, at_elems * sizeof(__nv_bfloat16), s));
+  EVC_TRY(launch_to_bf16(A, ldA, o->A16, o->ldA16, N, F, il, s));
+  EVC_TRY(launch_to_bf16(o->AT, o->ldN, o->AT16, o->ldN16, o->F_main, N, il, s));
+  const int cA = il ? o->ldA16 : F, cN = il ? o->ldN16 : N;  // tensor-map columns (interleaved: every column is data or zero)
+  EVC_TRY(make_tmap16(&o->tmA16, o->A16, o->a_rows, cA, o->ldA16, 64, 128));
+  EVC_TRY(make_tmap16(&o->tmAT16, o->AT16, o->at_rows, cN, o->ldN16, 64, 128));
+  EVC_TRY(make_tmap16(&o->tmAT16_s[0], o->AT16, o->at_rows, cN, o->ldN16, 64, 64));
+  EVC_TRY(make_tmap16(&o->tmAT16_s[1], o->AT16, o->at_rows, cN, o->ldN16, 64, 32));
   if (B) {
-    EVC_CUDA(cudaMalloc(&o->BT16, planes * at_elems * sizeof(__nv_bfloat16)));
-    EVC_CUDA(cudaMemsetAsync(o->BT16, 0, planes * at_elems * sizeof(__nv_bfloat16), s));
-    EVC_TRY(launch_to_bf16(o->BT, o->ldN, o->BT16, o->ldN16, o->F_main, N, planes == 2 ? at_elems : 0, s));
-    EVC_TRY(make_tmap16(&o->tmBT16, o->BT16, planes * o->at_rows, N, o->ldN16, bk, 128));
-    EVC_TRY(make_tmap16(&o->tmBT16_s[0], o->BT16, planes * o->at_rows, N, o->ldN16, bk, 64));
-    EVC_TRY(make_tmap16(&o->tmBT16_s[1], o->BT16, planes * o->at_rows, N, o->ldN16, bk, 32));
+    EVC_CUDA(cudaMalloc(&o->BT16, at_elems * sizeof(__nv_bfloat16)));
+    EVC_CUDA(cudaMemsetAsync(o->BT16, 0, at_elems * sizeof(__nv_bfloat16), s));
+    EVC_TRY(launch_to_bf16(o->BT, o->ldN, o->BT16, o->ldN16, o->F_main, N, il, s));
+    EVC_TRY(make_tmap16(&o->tmBT16, o->BT16, o->at_rows, cN, o->ldN16, 64, 128));
+    EVC_TRY(make_tmap16(&o->tmBT16_s[0], o->BT16, o->at_rows, cN, o->ldN16, 64, 64));
+    EVC_TRY(make_tmap16(&o->tmBT16_s[1], o->BT16, o->at_rows, cN, o->ldN16, 64, 32));
   }
   // the fp32 transposes were staging only (stream order: the conversions above read them first)
   EVC_CUDA(cudaFreeAsync(o->AT, s));
@@ -1705,9 +1720,8 @@ inline int left_ld(int T) { return round_up(T, kC2BlockT); }
 // Room for the K operand of contraction 2 (the ratio) in the mode's format; pad rows start out zero.
 inline int reserve_ratio(DictOperands& o, int mode, int T, cudaStream_t s) {
   if (mode != EVC_MODE_3XTF32 && mode != EVC_MODE_BF16) return EVC_OK;
-  const int planes = (mode == EVC_MODE_3XTF32) ? 2 : 1;
   const long long rows = plane_rows(T);
-  const size_t need = (size_t)planes * rows * o.ldA16 * sizeof(__nv_bfloat16);
+  const size_t need = (size_t)rows * o.ldA16 * sizeof(__nv_bfloat16);  // (ldA16: bf16 pitch, or both interleaved planes)
   if (need > o.r16.bytes || rows != o.r_rows) {
     EVC_TRY(o.r16.reserve(need));
     EVC_CUDA(cudaMemsetAsync(o.r16.p, 0, o.r16.bytes, s));
@@ -1718,7 +1732,7 @@ inline int reserve_ratio(DictOperands& o, int mode, int T, cudaStream_t s) {
 inline ROut ratio_out(DictOperands& o, int mode, float* R, int ldR) {
   ROut ro{};
   if (mode == EVC_MODE_3XTF32) {
-    ro.R12 = o.r16.as<__nv_bfloat16>(); ro.ldr12 = o.ldA16; ro.plane = (size_t)o.r_rows * o.ldA16;
+    ro.R12 = o.r16.as<__nv_bfloat16>(); ro.ldr12 = o.ldA16; ro.k12 = round_up(o.F, 32);
   } else if (mode == EVC_MODE_BF16) {
     ro.R16 = o.r16.as<__nv_bfloat16>(); ro.ldr16 = o.ldA16;
   } else {
@@ -1743,7 +1757,7 @@ inline int after_h_written(DictOperands& o, int mode, const float* H, int ldH, i
   if (mode == EVC_MODE_BF16) {
     // the bf16 shadow of these activations (afterwards the fused update keeps it current)
     EVC_TRY(o.h16.reserve((size_t)T * o.ldN16 * sizeof(__nv_bfloat16)));
-    EVC_TRY(launch_to_bf16(H, ldH, o.h16.as<__nv_bfloat16>(), o.ldN16, T, o.N, 0, s));
+    EVC_TRY(launch_to_bf16(H, ldH, o.h16.as<__nv_bfloat16>(), o.ldN16, T, o.N, false, s));
   }
   return EVC_OK;
 }
@@ -1781,7 +1795,6 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   p.splits_last = pl.splits_last; p.kblocks_per_split_last = pl.kb_per_split_last;
   p.items_main = (pl.splits_last ? pl.m_groups - 1 : pl.m_groups) * pl.t_tiles * pl.splits;
   p.half_from = p.items_main;
-  p.m_plane_rows = (int)o.at_rows; p.n_plane_rows = 0;
   p.out = partials; p.ld_out = pl.ldp;
   p.out_keep_l2 = getenv("EVC_NO_KEEP_L2") ? 0 : 1;
   // leftover rows (F_main..): in the fp32-accurate mode contraction 1's split warps carry them along (per-split sums
@@ -1920,18 +1933,16 @@ inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR
   if (kP > 1 && Launch::slots() <= 0)  // this device cannot co-schedule such clusters: plain pairs
     return contract2_p<kPrec, kEpi, 1, kMT>(o, mode, T, R, ldR, p, num0, s);
   const int bke = bk_elems(mode);
-  const int planes = (kPrec == PREC_SPLIT) ? 2 : 1;
   CUtensorMap tmR;
   // (clusters of kP pairs: every CTA fetches a 1/kP slice of its half of the frame tile and multicasts it)
   if (kPrec == PREC_TF32) EVC_TRY(make_tmap(&tmR, R, T, o.F, ldR, 32, kC2BlockT / kCG));
-  else EVC_TRY(make_tmap16(&tmR, o.r16.as<__nv_bfloat16>(), kPrec == PREC_SPLIT ? planes * o.r_rows : (long long)T, o.F,
-                           o.ldA16, bke, kC2BlockT / kCG / kP));
+  else EVC_TRY(make_tmap16(&tmR, o.r16.as<__nv_bfloat16>(), (long long)T, kPrec == PREC_SPLIT ? o.ldA16 : o.F, o.ldA16, 64,
+                           kC2BlockT / kCG / kP));
   p.M_total = o.N; p.T = T; p.K = o.F;
   // row groups of 256 exemplars, dealt to the pairs of a cluster in runs of kP: the work items are cluster-level
   p.num_m_groups = ceil_div(ceil_div(o.N, 128 * kMT * kCG), kP); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(o.F, bke); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
-  p.m_plane_rows = (int)o.a_rows; p.n_plane_rows = (int)o.r_rows;
   {
     // tail balancing: the tiles of a last, less-than-half-filled round run as two half-width items each
     const int slots = Launch::slots(), rem = p.items_main % slots;
