@@ -273,11 +273,15 @@ struct TileCfg {
   static constexpr int kNPlaneBytes = kNRows * kNRowBytes;               // kSplitN: one derived plane
   static constexpr int kNBytes = kSplitN ? 2 * kNPlaneBytes : kNRows * 128;
   static constexpr int kNPlaneOff = kSplitN ? kNPlaneBytes : 64;         // where the lo plane starts (split mode)
-  static constexpr int kRawBytes = kSplitN ? kNRows * 128 : 0;           // fp32 frame tile the planes are derived from
+  // kSplitN: the fp32 frame tile TMA brings; the two planes are derived IN PLACE (same 16 KB: every thread reads its
+  // quarter rows, a barrier, then writes), which buys a fourth ring stage -- with three the TMA -> split -> MMA chain
+  // left the tensor pipe idle 16 % of contraction 1's main loop
+  static constexpr int kRawBytes = kSplitN ? kNRows * 128 : 0;
+  static_assert(!kSplitN || kRawBytes == kNBytes, "in-place split: the planes take exactly the raw tile's bytes");
   // kSplitN: this K-block of the dictionary rows that stay off the tensor cores (F_main.., at most 8): [8][32] fp32
   static constexpr int kLeftBytes = kSplitN ? 8 * 128 : 0;
-  static constexpr int kOffN = kMBytes, kOffRaw = kMBytes + kNBytes, kOffLeft = kMBytes + kNBytes + kRawBytes;
-  static constexpr int kStageBytes = kMBytes + kNBytes + kRawBytes + kLeftBytes;
+  static constexpr int kOffN = kMBytes, kOffRaw = kMBytes, kOffLeft = kMBytes + kNBytes;
+  static constexpr int kStageBytes = kMBytes + kNBytes + kLeftBytes;
   // bytes per CTA per stage that TMA credits to the leader's "full" barrier
   static constexpr int kTxBytes = kMBytes + (kSplitN ? 0 : kNBytes);
   // arrivals on the leader's "full" barrier: its producer's expect_tx + (kSplitN) every split warp of both CTAs
@@ -318,6 +322,10 @@ __device__ __forceinline__ float quotient(float a, float d, float r) {
   return (q == q) ? q : q0;  // a*r overflowed or a is inf: keep the uncorrected value instead of inf - inf
 }
 
+// barrier among `threads` threads of the CTA (ids 1..: 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 // One frame tile of a ring stage: raw = [kRows x 32 fp32] as TMA wrote it with the 128B swizzle (16-byte chunk c
 // of row r sits at chunk c ^ (r & 7)); p1 / p2 = [kRows x 32 bf16] in the 64B-swizzle layout the MMA descriptors
 // expect (chunk c of row r at chunk c ^ ((r >> 1) & 3)).  A unit is a quarter row: 8 floats in, 16 + 16 bytes out;
@@ -356,6 +364,7 @@ __device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, ui
       }
     }
   }
+  named_bar_sync(1, kEpiWarps * 32);  // in place: every quarter row is in registers before any plane is written
 #pragma unroll
   for (int q = 0; q < kPer; ++q) {
     const int u = q * (kEpiWarps * 32) + tid, row = u >> 2, c = u & 3;
@@ -371,9 +380,6 @@ __device__ __forceinline__ void split_planes(const uint8_t* raw, uint8_t* p1, ui
 }
 
 // ---- split-K sum + ratio inside contraction 1 (FusedReduce) ------------------------------------------------------
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 __device__ __forceinline__ unsigned int atom_add_release_gpu(unsigned int* p, unsigned int v) {
   unsigned int old;
   asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");

@@ -1,4 +1,4 @@
 #!/bin/bash
-# ring depth A/B: default (5 operand stages + 4 H chunk buffers in contraction 2), 6 + 2, 4 + 4
+# contraction 2, shared memory split between operand stages and H chunk buffers: 5 + 4 (default), 4 + 6, 3 + 8
 out=gpurun_out; mkdir -p $out
-tools/ab_bench.sh "default:EVC_X=1" "hb2:EVC_LIB_PATH=build_variants/libevc_b200_hb2.so" "st4:EVC_LIB_PATH=build_variants/libevc_b200_st4.so" "default2:EVC_X=1" "hb2b:EVC_LIB_PATH=build_variants/libevc_b200_hb2.so"
+tools/ab_bench.sh "default:EVC_X=1" "s4h6:EVC_LIB_PATH=build_variants/libevc_b200_s4h6.so" "s3h8:EVC_LIB_PATH=build_variants/libevc_b200_s3h8.so" "default2:EVC_X=1" "s4h6b:EVC_LIB_PATH=build_variants/libevc_b200_s4h6.so"
