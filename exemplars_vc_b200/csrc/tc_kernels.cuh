@@ -142,9 +142,10 @@ struct GemmParams {
   // CTA pair carries the same number of MMAs.  items_main = work items of the other groups; 0 splits_last means
   // "no special last group".
   int items_main, splits_last, kblocks_per_split_last;
-  // Tail balancing of contraction 2: tiles with index >= half_from are processed as two half-width items (t_cols =
-  // kBlockT/2 frames each) so the last, partly filled round costs half a tile time.  half_from = items_main: off.
-  int half_from;
+  // Tail balancing of contraction 2: the tiles with index >= half_from (those of a last, partly filled round) are cut
+  // into tail_parts narrower items of whole 32-frame chunks each (plan_tail), so that round costs a fraction of a tile
+  // time.  half_from = items_main: off.
+  int half_from, tail_parts;
   int m_fastest;  // work-item order: 1 = consecutive CTA pairs take consecutive dictionary-row groups of one frame tile
   float* out;    // PARTIAL: [split][t][m] with pitch ld_out;  MU_*: the activations H (T, ld_out)
   int ld_out;
@@ -205,11 +206,13 @@ __host__ __device__ __forceinline__ WorkItem decode_item(const GemmParams& p, in
   w.t_off = 0;
   w.t_cols = block_t;
   if (item >= p.half_from && p.half_from < p.items_main) {
-    // half-width tail items of contraction 2 (no split-K there): tile = half_from + h/2, half = h & 1
-    const int h = item - p.half_from;
-    item = p.half_from + (h >> 1);
-    w.t_cols = block_t / 2;
-    w.t_off = (h & 1) * w.t_cols;
+    // narrow tail items of contraction 2 (no split-K there): tile = half_from + h / parts, piece = h % parts; the
+    // tile's 32-frame chunks are dealt to the pieces as evenly as possible (256 frames in 3 pieces: 96 + 96 + 64)
+    const int parts = p.tail_parts, h = item - p.half_from, part = h % parts;
+    item = p.half_from + h / parts;
+    const int chunks = block_t / 32, base = chunks / parts, extra = chunks % parts;
+    w.t_cols = (base + (part < extra ? 1 : 0)) * 32;
+    w.t_off = (part * base + (part < extra ? part : extra)) * 32;
   }
   if (item < p.items_main) {
     const int groups = p.splits_last ? p.num_m_groups - 1 : p.num_m_groups;
@@ -235,6 +238,21 @@ __host__ __device__ __forceinline__ WorkItem decode_item(const GemmParams& p, in
     w.kb1 = min(w.kb0 + p.kblocks_per_split_last, p.kblocks_total);
   }
   return w;
+}
+
+__host__ __device__ __forceinline__ int num_items_of(const GemmParams& p) {
+  return p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from) * (p.tail_parts - 1);
+}
+// The `rem` tiles of a last, partly filled round are cut into as many pieces (at most 4: 64 frames) as still fit ONE
+// extra round of the `slots` resident CTA pairs: 316 tiles on 74 pairs -> 20 tail tiles x 3 pieces, 0.375 instead of
+// 1 (whole tiles) or 0.5 (halves) tile times for the round.
+inline void plan_tail(GemmParams& p, int slots, int block_t, bool allow, int max_parts = 4) {
+  p.half_from = p.items_main;
+  p.tail_parts = 1;
+  const int rem = slots > 0 ? p.items_main % slots : 0;
+  if (!allow || p.items_main <= slots || rem <= 0) return;
+  const int parts = std::min(std::min(max_parts, block_t / 32), slots / rem);
+  if (parts >= 2) { p.half_from = p.items_main - rem; p.tail_parts = parts; }
 }
 
 constexpr int kCG = 2;          // CTAs per MMA (cta_group::2)
@@ -669,7 +687,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ 
   pdl_wait();
   pdl_launch_dependents();
 
-  const int num_items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
+  const int num_items = num_items_of(p);
   // all CTAs of a cluster walk the same (cluster-level) items; pair q takes its own share of each (item_of)
   const int first_item = blockIdx.x / (kCG * kP), item_stride = gridDim.x / (kCG * kP);
   auto item_of = [&](int item) {
@@ -1485,7 +1503,7 @@ struct TcLaunch {
     auto kern = tc_gemm_kernel<kMTiles, kBlockT, kPrec, kSplitN, kEpi, kP, kShareM>;
     const int nslots = slots();
     if (nslots <= 0) return fail(EVC_ERR_UNSUPPORTED, "clusters of %d CTA pairs cannot be scheduled on this device", kP);
-    const int items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
+    const int items = num_items_of(p);
     if (items <= 0) return EVC_OK;
     const int grid = (items < nslots ? items : nslots) * kCG * kP;
     cudaLaunchConfig_t cfg{};
@@ -1800,7 +1818,7 @@ inline int contract_wh_t(DictOperands& o, int mode, const float* H, int ldH, int
   p.kblocks_per_split = pl.kb_per_split; p.kblocks_total = pl.kb_total;
   p.splits_last = pl.splits_last; p.kblocks_per_split_last = pl.kb_per_split_last;
   p.items_main = (pl.splits_last ? pl.m_groups - 1 : pl.m_groups) * pl.t_tiles * pl.splits;
-  p.half_from = p.items_main;
+  p.half_from = p.items_main; p.tail_parts = 1;
   p.out = partials; p.ld_out = pl.ldp;
   p.out_keep_l2 = getenv("EVC_NO_KEEP_L2") ? 0 : 1;
   // leftover rows (F_main..): in the fp32-accurate mode contraction 1's split warps carry them along (per-split sums
@@ -1950,10 +1968,10 @@ inline int contract2_p(DictOperands& o, int mode, int T, const float* R, int ldR
   p.kblocks_total = ceil_div(o.F, bke); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
   {
-    // tail balancing: the tiles of a last, less-than-half-filled round run as two half-width items each
-    const int slots = Launch::slots(), rem = p.items_main % slots;
+    // tail balancing: the tiles of a last, partly filled round run as 2-4 narrower items each
     static const bool allow = getenv("EVC_NO_HALF_TILES") == nullptr;
-    p.half_from = (allow && p.items_main > slots && rem > 0 && 2 * rem <= slots) ? p.items_main - rem : p.items_main;
+    static const int max_parts = getenv("EVC_TAIL_PARTS") ? std::max(2, atoi(getenv("EVC_TAIL_PARTS"))) : 4;
+    plan_tail(p, Launch::slots(), kC2BlockT, allow, max_parts);
   }
   // neighbouring CTA pairs update neighbouring 512-byte runs of the same H rows: DRAM pages stay open
   p.m_fastest = 1;

@@ -37,8 +37,8 @@ static void check_c1(int F_main, int N, int T, int bke, int pairs = 1, int slots
   p.kblocks_per_split = pl.kb_per_split; p.kblocks_total = pl.kb_total;
   p.splits_last = pl.splits_last; p.kblocks_per_split_last = pl.kb_per_split_last;
   p.items_main = (pl.splits_last ? pl.m_groups - 1 : pl.m_groups) * pl.t_tiles * pl.splits;
-  p.half_from = p.items_main;
-  const int items = p.items_main + p.splits_last * p.num_t_tiles + (p.items_main - p.half_from);
+  p.half_from = p.items_main; p.tail_parts = 1;
+  const int items = num_items_of(p);
   CHECK(items > 0, "F=%d N=%d T=%d", F_main, N, T);
   CHECK(pl.kb_total == ceil_div(N, bke), "kb_total");
   std::map<std::pair<int, int>, std::vector<char>> cover;
@@ -71,24 +71,29 @@ static void check_c2(int N, int T, int F, int bke) {
   p.num_m_groups = ceil_div(N, 128 * kC2MTiles * kCG); p.num_t_tiles = ceil_div(T, kC2BlockT); p.num_splits = 1;
   p.kblocks_total = ceil_div(F, bke); p.kblocks_per_split = p.kblocks_total;
   p.items_main = p.num_m_groups * p.num_t_tiles; p.splits_last = 0; p.kblocks_per_split_last = 0;
-  const int slots = num_sms() / kCG, rem = p.items_main % slots;
-  p.half_from = (p.items_main > slots && rem > 0 && 2 * rem <= slots) ? p.items_main - rem : p.items_main;
+  const int slots = num_sms() / kCG;
+  plan_tail(p, slots, kC2BlockT, true);
   for (int m_fastest = 0; m_fastest < 2; ++m_fastest) {
     p.m_fastest = m_fastest;
-    const int items = p.items_main + (p.items_main - p.half_from);
+    const int items = num_items_of(p);
     std::map<std::pair<int, int>, int> cols;
+    std::map<std::pair<int, int>, unsigned> chunk_mask;
     for (int it = 0; it < items; ++it) {
       const WorkItem w = decode_item(p, it, kC2BlockT);
       CHECK(w.kb0 == 0 && w.kb1 == p.kblocks_total, "whole K per item");
       CHECK(w.m_group >= 0 && w.m_group < p.num_m_groups && w.t_tile >= 0 && w.t_tile < p.num_t_tiles, "range");
-      CHECK(w.t_cols == kC2BlockT || w.t_cols == kC2BlockT / 2, "t_cols %d", w.t_cols);
-      CHECK(w.t_off % w.t_cols == 0 && w.t_off + w.t_cols <= kC2BlockT, "t_off %d", w.t_off);
+      CHECK(w.t_cols >= 64 && w.t_cols <= kC2BlockT && w.t_cols % 32 == 0, "t_cols %d", w.t_cols);
+      CHECK(w.t_off % 32 == 0 && w.t_off + w.t_cols <= kC2BlockT, "t_off %d", w.t_off);
       CHECK(w.t_cols % kHChunkT == 0, "items are whole H chunks");
       cols[{w.m_group, w.t_tile}] += w.t_cols;
+      for (int c = w.t_off / 32; c < (w.t_off + w.t_cols) / 32; ++c) {  // every chunk of a tile exactly once
+        CHECK(!(chunk_mask[{w.m_group, w.t_tile}] & (1u << c)), "chunk %d of tile (%d,%d) twice", c, w.m_group, w.t_tile);
+        chunk_mask[{w.m_group, w.t_tile}] |= 1u << c;
+      }
     }
     CHECK((int)cols.size() == p.items_main, "tiles covered %d of %d (N=%d T=%d)", (int)cols.size(), p.items_main, N, T);
     for (auto& kv : cols) CHECK(kv.second == kC2BlockT, "tile (%d,%d) got %d frame columns", kv.first.first, kv.first.second, kv.second);
-    // balance: no CTA (pair) carries more than one half tile above the mean
+    // balance: no CTA (pair) carries more than one tile above the mean
     std::vector<double> load(slots, 0.0);
     for (int it = 0; it < items; ++it) load[it % slots] += decode_item(p, it, kC2BlockT).t_cols / (double)kC2BlockT;
     double mx = 0, sum = 0;
