@@ -587,9 +587,16 @@ __device__ __forceinline__ void fused_reduce_phase(const GemmParams& p, const CU
       for (int f = F_main + t64, it = 0; f < r.cols; f += kRedThreads, ++it) {
         const bool have = f < r.F && (r.left_rows > 0 || r.Lp);
         float sum = 0.f;
-        if (have && r.Lp)
-          for (int kk = 0; kk < r.lp_splits; ++kk) sum += __ldcg(r.Lp + ((size_t)kk * r.n_left + (f - F_main)) * r.left_ld + t);
-        else if (have) sum = s_left[f - F_main];
+        if (have && r.Lp) {
+          for (int k0 = 0; k0 < r.lp_splits; k0 += 8) {  // eight loads in flight, added in split order
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = (k0 + e < r.lp_splits) ? __ldcg(r.Lp + ((size_t)(k0 + e) * r.n_left + (f - F_main)) * r.left_ld + t) : 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (k0 + e < r.lp_splits) sum += v[e];
+          }
+        } else if (have) sum = s_left[f - F_main];
         if (f < r.ldwh && (have || f >= r.F)) r.WH[(size_t)t * r.ldwh + f] = sum;
         if (r.X) store_r(r.ro, t, f, have ? __fdiv_rn(it == 0 ? x_tail_now : r.X[(size_t)t * r.ldx + f], fmaxf(sum, p.eps)) : 0.f);
       }
@@ -1232,7 +1239,14 @@ reduce_partials_kernel(const __grid_constant__ CUtensorMap tmP,  // P as a (colu
     bool have = false;
     if (f < F_main) { s = sv[j]; have = true; }
     else if (f < F && Lp) {  // rows kept off the tensor cores: contraction 1's per-split sums [split][row][frame]
-      for (int k = 0; k < lp_splits; ++k) s += __ldcg(Lp + ((size_t)k * n_left + (f - F_main)) * left_ld + t);
+      for (int k0 = 0; k0 < lp_splits; k0 += 8) {  // eight loads in flight, added in split order
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          v[e] = (k0 + e < lp_splits) ? __ldcg(Lp + ((size_t)(k0 + e) * n_left + (f - F_main)) * left_ld + t) : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (k0 + e < lp_splits) s += v[e];
+      }
       have = true;
     }
     else if (f < F && left_rows > 0) { s = s_left[f - F_main]; have = true; }
