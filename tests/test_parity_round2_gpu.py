@@ -235,3 +235,29 @@ def test_in_kernel_split_k_sum_equals_the_separate_reduction_pass():
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append([l for l in r.stdout.splitlines() if " H " in l])
     assert len(outs[0]) == 18 and outs[0] == outs[1], "\n".join(f"{a}\n{b}" for a, b in zip(*outs) if a != b)
+
+
+ODD_SHAPES = [(64, 128, 1), (65, 129, 33), (136, 1000, 257), (200, 333, 100), (513, 700, 300), (513, 4100, 513),
+              (641, 2049, 70), (1025, 520, 260), (257, 200, 19200), (2565, 1300, 40), (520, 130, 5)]
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "tf32", "bf16"])
+def test_odd_shapes_against_the_exact_fp32_kernels(mode):
+    """Ragged shapes through the tensor-core kernels against the exact-fp32 CUDA-core kernels of the same library
+    (an independent implementation of the same update, sklearn _nmf.py:521-626): leftover dictionary rows 0, 1, 5 and
+    8 (F = 200 / 513, 641, 1025, 257 / 2565 / 136, 520), several dictionary-row groups, exemplar and frame counts
+    that fill no tile, one frame, K split and not split (T = 19200: the ratio leaves straight from TMEM), narrow tail
+    items.  Five iterations from the sklearn initialisation; H and Y within the mode's tolerance."""
+    from exemplars_vc_b200 import ExemplarDictionary, synth
+    tol = {"3xtf32": 1e-3, "tf32": 2e-2, "bf16": 3e-2}[mode]
+    for F, N, T in ODD_SHAPES:
+        A, B = synth.dictionaries(1000 + F + N, F, N)
+        X = synth.frames(2000 + T, A, T)
+        res = {}
+        for m in ("fp32", mode):
+            with ExemplarDictionary(A, B, mode=m) as d:
+                act = d.solve(X, tol=0.0, max_iter=5)
+                res[m] = (d.to_host(act.H), d.to_host(d.convert(act.H)), act.objective)
+        eh, ey = rel_fro(res[mode][0], res["fp32"][0]), rel_fro(res[mode][1], res["fp32"][1])
+        eo = abs(res[mode][2] - res["fp32"][2]) / max(res["fp32"][2], 1e-30)
+        assert eh < tol and ey < tol and eo < tol, (mode, (F, N, T), eh, ey, eo)
